@@ -1,0 +1,196 @@
+"""pyoracle.py -- TEST INFRASTRUCTURE: ctypes access to oracle/liboracle.so (the C restatement,
+pt_oracle.c) and subprocess access to the reference's own binaries under oracle/_ref/
+(ref_build/build_ref.sh).  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs import this module; the product never does.
+"""
+import ctypes
+import json
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liboracle.so")
+REF_DIR = os.path.join(HERE, "_ref")
+
+PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_V4 = 0, 1, 2
+ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
+SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
+
+
+class OracleParams(ctypes.Structure):
+    _fields_ = [
+        ("profile", ctypes.c_int),
+        ("width", ctypes.c_int),
+        ("height", ctypes.c_int),
+        ("num_tiles_x", ctypes.c_int),
+        ("num_tiles_y", ctypes.c_int),
+        ("num_bounces", ctypes.c_int),
+        ("env_kind", ctypes.c_int),
+        ("env_sampler", ctypes.c_int),
+        ("env", ctypes.POINTER(ctypes.c_float)),
+        ("env_width", ctypes.c_int),
+        ("env_height", ctypes.c_int),
+    ]
+
+
+class OracleCounters(ctypes.Structure):
+    _fields_ = [("paths", ctypes.c_uint64), ("segments", ctypes.c_uint64), ("escapes", ctypes.c_uint64)]
+
+
+_lib = None
+
+
+def build():
+    subprocess.run(["make", "-C", HERE, "liboracle.so"], check=True, capture_output=True)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        L = ctypes.CDLL(LIB_PATH)
+        L.oracle_render.argtypes = [ctypes.POINTER(OracleParams), ctypes.POINTER(ctypes.c_float), ctypes.c_int,
+                                    ctypes.c_int, ctypes.c_int, ctypes.POINTER(OracleCounters)]
+        L.oracle_render.restype = ctypes.c_int
+        L.oracle_path_radiance.argtypes = [ctypes.POINTER(OracleParams), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                           ctypes.POINTER(ctypes.c_float)]
+        L.oracle_wang_hash.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
+        L.oracle_wang_hash.restype = ctypes.c_uint32
+        L.oracle_random01.argtypes = [ctypes.POINTER(ctypes.c_uint32)]
+        L.oracle_random01.restype = ctypes.c_float
+        L.oracle_seed.argtypes = [ctypes.c_int] * 3
+        L.oracle_seed.restype = ctypes.c_uint32
+        L.oracle_final_rng_state.argtypes = [ctypes.POINTER(OracleParams), ctypes.c_int, ctypes.c_int, ctypes.c_int]
+        L.oracle_final_rng_state.restype = ctypes.c_uint32
+        L.oracle_buffer_index.argtypes = [ctypes.c_int] * 7
+        L.oracle_buffer_index.restype = ctypes.c_int64
+        L.oracle_resolve_ldr.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                         ctypes.c_int, ctypes.POINTER(ctypes.c_uint32), ctypes.c_int]
+        L.oracle_camera_distance.restype = ctypes.c_float
+        _lib = L
+    return _lib
+
+
+def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=ENV_NONE, env_sampler=SAMPLER_POINT):
+    p = OracleParams()
+    p.profile, p.width, p.height = profile, width, height
+    p.num_tiles_x, p.num_tiles_y, p.num_bounces = ntx, nty, bounces
+    p.env_kind, p.env_sampler = env_kind, env_sampler
+    keep = None
+    if env is not None:
+        keep = np.ascontiguousarray(env, dtype=np.float32)
+        assert keep.ndim == 3 and keep.shape[2] == 3
+        p.env = keep.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+        p.env_height, p.env_width = keep.shape[0], keep.shape[1]
+    return p, keep
+
+
+def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, env=None, env_kind=ENV_NONE,
+           env_sampler=SAMPLER_POINT, target=None, nthreads=0):
+    """Returns (tile-major f32 buffer, counters dict)."""
+    p, keep = make_params(profile, width, height, ntx, nty, bounces, env, env_kind, env_sampler)
+    if target is None:
+        target = np.zeros(width * height * 3, dtype=np.float32)
+    else:
+        target = np.ascontiguousarray(target, dtype=np.float32).copy()
+    cnt = OracleCounters()
+    rc = lib().oracle_render(ctypes.byref(p), target.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), first_frame,
+                             nframes, nthreads, ctypes.byref(cnt))
+    if rc != 0:
+        raise ValueError("oracle_render: invalid parameters")
+    del keep
+    return target, {"paths": cnt.paths, "segments": cnt.segments, "escapes": cnt.escapes}
+
+
+def resolve_ldr(target, width, height, ntx, nty, mode=0):
+    t = np.ascontiguousarray(target, dtype=np.float32)
+    out = np.zeros(width * height, dtype=np.uint32)
+    rc = lib().oracle_resolve_ldr(t.ctypes.data_as(ctypes.POINTER(ctypes.c_float)), width, height, ntx, nty,
+                                  out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), mode)
+    if rc != 0:
+        raise ValueError("oracle_resolve_ldr: invalid parameters")
+    return out.reshape(height, width)
+
+
+def detile(buf, width, height, ntx, nty):
+    """tile-major SoA8 accumulation buffer -> (H, W, 3) row-major image (row 0 = top)."""
+    tw, th = width // ntx, height // nty
+    a = np.asarray(buf, dtype=np.float32).reshape(nty, ntx, th, tw // 8, 3, 8)
+    return np.ascontiguousarray(a.transpose(0, 2, 1, 3, 5, 4).reshape(height, width, 3))
+
+
+def tile(img, ntx, nty):
+    """(H, W, 3) row-major image -> tile-major SoA8 buffer."""
+    h, w, _ = img.shape
+    tw, th = w // ntx, h // nty
+    a = np.asarray(img, dtype=np.float32).reshape(nty, th, ntx, tw // 8, 8, 3)
+    return np.ascontiguousarray(a.transpose(0, 2, 1, 3, 5, 4)).reshape(-1)
+
+
+# ---- reference binaries ---------------------------------------------------------------------
+def ref_binary(name):
+    path = os.path.join(REF_DIR, name)
+    return path if os.path.exists(path) else None
+
+
+def run_ref(name, width, height, ntx, nty, frames, bounces=None, env=None, threads=None, start_frame=0,
+            target=None, time_it=False, warmup=0, ldr=False, timeout=3600):
+    """Runs oracle/_ref/<name>; returns dict(buffer=..., timing=..., ldr=...)."""
+    exe = ref_binary(name)
+    if exe is None:
+        raise FileNotFoundError(f"{name} not built (oracle/ref_build/build_ref.sh needs /root/reference)")
+    with tempfile.TemporaryDirectory() as td:
+        out = os.path.join(td, "out.f32")
+        cmd = [exe, "--w", str(width), "--h", str(height), "--ntx", str(ntx), "--nty", str(nty), "--frames",
+               str(frames), "--out", out, "--start-frame", str(start_frame), "--warmup", str(warmup)]
+        if bounces is not None:
+            cmd += ["--bounces", str(bounces)]
+        if threads is not None:
+            cmd += ["--threads", str(threads)]
+        if env is not None:
+            e = np.ascontiguousarray(env, dtype=np.float32)
+            ep = os.path.join(td, "env.f32")
+            e.tofile(ep)
+            cmd += ["--env", ep, "--envw", str(e.shape[1]), "--envh", str(e.shape[0])]
+        if target is not None:
+            ip = os.path.join(td, "in.f32")
+            np.ascontiguousarray(target, dtype=np.float32).tofile(ip)
+            cmd += ["--in", ip]
+        if time_it:
+            cmd += ["--time"]
+        lp = os.path.join(td, "ldr.u32")
+        if ldr:
+            cmd += ["--ldr", lp]
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        if r.returncode != 0:
+            raise RuntimeError(f"{name} failed: {r.stderr}")
+        res = {"buffer": np.fromfile(out, dtype=np.float32)}
+        if time_it:
+            res["timing"] = json.loads(r.stdout.strip().splitlines()[-1])
+        if ldr:
+            res["ldr"] = np.fromfile(lp, dtype=np.uint32).reshape(height, width)
+        return res
+
+
+def synthetic_env(width, height):
+    """Deterministic synthetic equirect/cubemap-atlas texture:
+    texel(r,c,ch) = 0.05 + 4*u^2 with u = Randomf3201(wang_hash stream seeded 1|((r*W+c)*3+ch)),
+    plus a 'sun' disc of value 50 at uv (0.25, 0.75), radius 0.02 (in uv units)."""
+    idx = (np.arange(width * height * 3, dtype=np.uint64)).astype(np.uint32) | np.uint32(1)
+    s = idx.copy()
+    s = (s ^ np.uint32(61)) ^ (s >> np.uint32(16))
+    s = s * np.uint32(9)
+    s = s ^ (s >> np.uint32(4))
+    s = s * np.uint32(0x27D4EB2D)
+    s = s ^ (s >> np.uint32(15))
+    u = (s & np.uint32(0x7FFFFFFF)).astype(np.int32).astype(np.float32) / np.float32(2147483648.0)
+    tex = (np.float32(0.05) + np.float32(4.0) * u * u).astype(np.float32).reshape(height, width, 3)
+    rr, cc = np.meshgrid(np.arange(height), np.arange(width), indexing="ij")
+    du = (cc + 0.5) / width - 0.25
+    dv = (rr + 0.5) / height - 0.75
+    tex[(du * du + dv * dv) < 0.02 * 0.02] = np.float32(50.0)
+    return tex

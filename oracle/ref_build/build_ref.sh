@@ -1,0 +1,70 @@
+#!/usr/bin/env bash
+# build_ref.sh -- TEST INFRASTRUCTURE.  Compiles the reference's own renderer sources IN PLACE
+# (from $REF, default /root/reference/CPUPerformanceRayTracer) into command-line binaries under
+# oracle/_ref/ (git-ignored, shipped to the GPU box with the snapshot).  Nothing is copied:
+# each translation unit is streamed through sed into g++'s stdin.  The only edits, all declared:
+#   * "const int c_numBounces = N;"  -> "int c_numBounces = N;"      (harness sets --bounces)
+#   * "static f32 iFrame = 0.f;"     -> "f32 iFrame = 0.f;"          (harness sets --start-frame)
+#   * NUM_THREADS                    -> oracle_num_threads            (harness sets --threads)
+#   * v4 only: the compile-time switches of global_preprocessor_flags.h:56-66 that pick the env
+#     sampler / per-tile screen output are renamed ORACLE_<name> and set with -D, because that
+#     header is found next to the including file and cannot be overridden from outside.
+# No algorithmic edit.  Usage: build_ref.sh [outdir]
+set -euo pipefail
+HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
+REF="${REF:-/root/reference/CPUPerformanceRayTracer}"
+OUT="${1:-$HERE/../_ref}"
+CXX="${CXX:-g++}"
+mkdir -p "$OUT/obj"
+if [ ! -f "$REF/demofox_path_tracing_v2.cpp" ]; then
+    echo "build_ref.sh: reference sources not found at $REF (expected on the GPU box); keeping prebuilt $OUT" >&2
+    exit 0
+fi
+
+BASE="-std=c++17 -O2 -mavx2 -mfma -fno-operator-names -fpermissive -w -I$HERE/stubs -I$HERE -I$HERE/.. -I$REF"
+flags_for_mode() { if [ "$1" = exact ]; then echo "-DORACLE_EXACT=1 -ffp-contract=off"; else echo "-DORACLE_EXACT=0"; fi; }
+
+PATCH=(-E
+  -e 's/^const int c_numBounces = ([0-9]+);/int c_numBounces = \1;/'
+  -e 's/^static f32 iFrame = 0\.f;/f32 iFrame = 0.f;/'
+  -e 's/\bNUM_THREADS\b/oracle_num_threads/g'
+  -e 's/^#if USE_ENV_CUBEMAP/#if ORACLE_USE_ENV_CUBEMAP/'
+  -e 's/^#if USE_RANDOM_JITTER_TEXTURE_SAMPLING/#if ORACLE_USE_RANDOM_JITTER_TEXTURE_SAMPLING/'
+  -e 's/^#if OUTPUT_TO_SCREEN/#if ORACLE_OUTPUT_TO_SCREEN/')
+
+compile_stream() { # $1=source file in $REF, $2=object, rest=flags
+    local src="$1" obj="$2"; shift 2
+    { echo '#include "shim.h"'; sed "${PATCH[@]}" "$REF/$src"; } | $CXX $BASE "$@" -x c++ -c - -o "$obj"
+}
+
+build_variant() { # $1=binary name $2=variant id $3=variant source $4=mode, rest=extra -D
+    local name="$1" vid="$2" src="$3" mode="$4"; shift 4
+    local mf; mf="$(flags_for_mode "$mode")"
+    local o="$OUT/obj/$name"
+    compile_stream "$src" "$o.variant.o" $mf "$@"
+    compile_stream texture.cpp "$o.texture.o" $mf "$@"
+    compile_stream work_queue.cpp "$o.wq.o" $mf "$@"
+    $CXX $BASE $mf -DORACLE_VARIANT="$vid" -include "$HERE/shim.h" -c "$HERE/harness.cpp" -o "$o.harness.o"
+    $CXX -o "$OUT/$name" "$o.variant.o" "$o.texture.o" "$o.wq.o" "$o.harness.o" -lpthread -lm
+    echo "built $OUT/$name"
+}
+
+V4_EQ_RAND="-DORACLE_USE_ENV_CUBEMAP=0 -DORACLE_USE_RANDOM_JITTER_TEXTURE_SAMPLING=1 -DORACLE_OUTPUT_TO_SCREEN=0"
+V4_EQ_BILIN="-DORACLE_USE_ENV_CUBEMAP=0 -DORACLE_USE_RANDOM_JITTER_TEXTURE_SAMPLING=0 -DORACLE_OUTPUT_TO_SCREEN=0"
+V4_CUBE_RAND="-DORACLE_USE_ENV_CUBEMAP=1 -DORACLE_USE_RANDOM_JITTER_TEXTURE_SAMPLING=1 -DORACLE_OUTPUT_TO_SCREEN=0"
+V4_CUBE_BILIN="-DORACLE_USE_ENV_CUBEMAP=1 -DORACLE_USE_RANDOM_JITTER_TEXTURE_SAMPLING=0 -DORACLE_OUTPUT_TO_SCREEN=0"
+
+for mode in exact asis; do
+    build_variant "ref_v2_$mode" 1 demofox_path_tracing_v2.cpp "$mode" &
+    build_variant "ref_simt_textured_$mode" 2 demofox_path_tracing_simt_textured.cpp "$mode" &
+    build_variant "ref_v4_equirect_random_$mode" 3 demofox_path_tracing_optimization_v4.cpp "$mode" $V4_EQ_RAND &
+    build_variant "ref_v4_cubemap_random_$mode" 3 demofox_path_tracing_optimization_v4.cpp "$mode" $V4_CUBE_RAND &
+    for j in $(jobs -p); do wait "$j"; done
+done
+build_variant ref_v4_equirect_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_BILIN &
+build_variant ref_v4_cubemap_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_CUBE_BILIN &
+# the reference's asset loader (stb_image / stb_image_write, vendored in the reference tree)
+$CXX $BASE -DORACLE_EXACT=1 -include "$HERE/shim.h" "$HERE/asset_tool.cpp" "$REF/asset_loading.cpp" -o "$OUT/ref_asset_tool" -lm &
+for j in $(jobs -p); do wait "$j"; done
+rm -rf "$OUT/obj"
+echo "reference binaries in $OUT"

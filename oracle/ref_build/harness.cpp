@@ -1,0 +1,138 @@
+/*
+ * harness.cpp -- TEST INFRASTRUCTURE.  Command-line driver around the reference's own render
+ * entry points, linked against the reference sources compiled in place (build_ref.sh).  It
+ * mirrors what ApplicationState::RenderOffline does around Render() (Application.cpp:400-458):
+ * allocate + zero the f32 target (Application.cpp:141-151), call the entry once per frame,
+ * optionally time the calls, dump the raw accumulation buffer.
+ *
+ *   -DORACLE_VARIANT=1  DemofoxRenderV2            (demofox_path_tracing_v2.h:8-10)
+ *   -DORACLE_VARIANT=2  DemofoxRenderSimtTextured  (demofox_path_tracing_simt_textured.h:8-10)
+ *   -DORACLE_VARIANT=3  DemofoxRenderOptV4 (+ CopyOutputToFile)
+ *                       (demofox_path_tracing_optimization_v4.h:14-26)
+ *
+ * One process = one render job: the reference keeps the frame counter, scene and thread pool in
+ * file-scope statics and its worker threads never exit (work_queue.cpp:72-78).
+ */
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "texture.h"
+
+int oracle_num_threads = 8;  /* substituted for NUM_THREADS by build_ref.sh */
+extern int c_numBounces;     /* "const int c_numBounces = N;" made assignable by build_ref.sh */
+extern f32 iFrame;           /* "static f32 iFrame = 0.f;" made visible by build_ref.sh */
+
+#if ORACLE_VARIANT == 1
+void DemofoxRenderV2(f32*, i32, i32, i32, i32, i32, i32, i32, texture);
+#define ORACLE_RENDER(buf, W, H, ntx, nty, tw, th, tex, scr) DemofoxRenderV2(buf, W, H, ntx, nty, tw, th, 3, tex)
+#elif ORACLE_VARIANT == 2
+void DemofoxRenderSimtTextured(f32*, i32, i32, i32, i32, i32, i32, i32, texture);
+#define ORACLE_RENDER(buf, W, H, ntx, nty, tw, th, tex, scr) DemofoxRenderSimtTextured(buf, W, H, ntx, nty, tw, th, 3, tex)
+#elif ORACLE_VARIANT == 3
+void DemofoxRenderOptV4(f32*, i32, i32, i32, i32, i32, i32, i32, texture, void*);
+void CopyOutputToFile(f32*, i32, i32, i32, i32, i32, i32, i32, texture, void*);
+void InitializeGlobalRenderResources();
+#define ORACLE_RENDER(buf, W, H, ntx, nty, tw, th, tex, scr) DemofoxRenderOptV4(buf, W, H, ntx, nty, tw, th, 3, tex, scr)
+#else
+#error "ORACLE_VARIANT must be 1, 2 or 3"
+#endif
+
+static bool read_file(const char* path, void* dst, size_t bytes)
+{
+    FILE* f = fopen(path, "rb");
+    if (!f) return false;
+    size_t n = fread(dst, 1, bytes, f);
+    fclose(f);
+    return n == bytes;
+}
+static bool write_file(const char* path, const void* src, size_t bytes)
+{
+    FILE* f = fopen(path, "wb");
+    if (!f) return false;
+    size_t n = fwrite(src, 1, bytes, f);
+    fclose(f);
+    return n == bytes;
+}
+
+int main(int argc, char** argv)
+{
+    int W = 512, H = 512, ntx = 2, nty = 4, frames = 1, warmup = 0, start_frame = 0;
+    int envw = 0, envh = 0, do_time = 0, bounces = -1;
+    const char *env_path = 0, *out_path = 0, *in_path = 0, *ldr_path = 0;
+    for (int i = 1; i < argc; i++) {
+        std::string a = argv[i];
+        auto next = [&]() -> const char* { return (i + 1 < argc) ? argv[++i] : ""; };
+        if (a == "--w") W = atoi(next());
+        else if (a == "--h") H = atoi(next());
+        else if (a == "--ntx") ntx = atoi(next());
+        else if (a == "--nty") nty = atoi(next());
+        else if (a == "--frames") frames = atoi(next());
+        else if (a == "--warmup") warmup = atoi(next());
+        else if (a == "--start-frame") start_frame = atoi(next());
+        else if (a == "--bounces") bounces = atoi(next());
+        else if (a == "--threads") oracle_num_threads = atoi(next());
+        else if (a == "--env") env_path = next();
+        else if (a == "--envw") envw = atoi(next());
+        else if (a == "--envh") envh = atoi(next());
+        else if (a == "--out") out_path = next();
+        else if (a == "--in") in_path = next();
+        else if (a == "--ldr") ldr_path = next();
+        else if (a == "--time") do_time = 1;
+        else { fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
+    }
+    if (W % ntx || H % nty || (W / ntx) % 8) { fprintf(stderr, "invalid tiling\n"); return 2; }
+    if (oracle_num_threads < 1) oracle_num_threads = 1; /* v4 spawns NUM_THREADS-1 workers + the caller */
+    if (bounces >= 0) c_numBounces = bounces;
+    iFrame = (f32)start_frame;
+    const int tw = W / ntx, th = H / nty;
+
+    texture tex;
+    std::vector<f32> env;
+    if (env_path) {
+        env.resize((size_t)envw * envh * 3);
+        if (!read_file(env_path, env.data(), env.size() * 4)) { fprintf(stderr, "cannot read env\n"); return 3; }
+        tex.Data = env.data();
+        tex.Width = envw;
+        tex.Height = envh;
+        tex.Components = 3;
+    }
+
+    const size_t nfloats = (size_t)W * H * 3;
+    f32* target = (f32*)aligned_alloc(64, (nfloats * 4 + 63) / 64 * 64);
+    unsigned char* screen = (unsigned char*)aligned_alloc(64, ((size_t)W * H * 4 + 63) / 64 * 64);
+    memset(target, 0, nfloats * 4);
+    memset(screen, 0, (size_t)W * H * 4);
+    if (in_path && !read_file(in_path, target, nfloats * 4)) { fprintf(stderr, "cannot read --in\n"); return 3; }
+
+    for (int f = 0; f < warmup; f++) ORACLE_RENDER(target, W, H, ntx, nty, tw, th, tex, screen);
+    auto t0 = std::chrono::steady_clock::now();
+    for (int f = 0; f < frames; f++) ORACLE_RENDER(target, W, H, ntx, nty, tw, th, tex, screen);
+    auto t1 = std::chrono::steady_clock::now();
+    double sec = std::chrono::duration<double>(t1 - t0).count();
+
+    if (do_time) {
+        printf("{\"seconds\": %.6f, \"frames\": %d, \"warmup\": %d, \"width\": %d, \"height\": %d, "
+               "\"mpaths_per_s\": %.4f, \"ms_per_frame\": %.4f, \"threads\": %d, \"bounces\": %d}\n",
+               sec, frames, warmup, W, H, (double)W * H * frames / sec * 1e-6, sec * 1e3 / frames,
+               oracle_num_threads, c_numBounces);
+    }
+    if (out_path && !write_file(out_path, target, nfloats * 4)) { fprintf(stderr, "cannot write --out\n"); return 4; }
+#if ORACLE_VARIANT == 3
+    if (ldr_path) {
+        /* CopyOutputToFile enqueues tone-map jobs through the generic queue API, but v4's worker
+         * threads ignore the callback and re-render the tile instead.  Only
+         * with --threads 1 (zero workers: the caller drains the queue through CompleteAllWork, which
+         * does honour the callback) is the LDR output deterministic; the tests use that. */
+        CopyOutputToFile(target, W, H, ntx, nty, tw, th, 3, tex, screen);
+        if (!write_file(ldr_path, screen, (size_t)W * H * 4)) { fprintf(stderr, "cannot write --ldr\n"); return 4; }
+    }
+#else
+    (void)ldr_path;
+#endif
+    fflush(stdout);
+    _Exit(0); /* worker threads never exit */
+}
