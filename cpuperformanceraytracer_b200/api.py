@@ -1,0 +1,256 @@
+"""api.py -- Python binding (ctypes) of the C ABI in include/b200pt.h.
+
+The product is libb200pt.so (hand-written sm_100a kernels behind a C ABI); this module is only
+the thin host-side handle used by the tests, bench.py and the multi-GPU driver.  It never renders
+on the CPU: importing it without the built library, or creating a Renderer without a B200,
+raises.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libb200pt.so")
+
+PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_OPT_V4 = 0, 1, 2
+MATH_PARITY, MATH_FAST = 0, 1
+ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
+SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
+ACCUM_RUNNING_AVERAGE, ACCUM_SUM = 0, 1
+LDR_FILE_RGBA, LDR_SCREEN_BGRA = 0, 1
+
+# every symbol include/b200pt.h declares (tests/test_abi.py checks the library exports them all)
+ABI_SYMBOLS = [
+    "b200pt_api_version", "b200pt_error_string", "b200pt_last_error", "b200pt_default_params", "b200pt_create",
+    "b200pt_destroy", "b200pt_set_env", "b200pt_resize", "b200pt_reset", "b200pt_set_frame_counter",
+    "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
+    "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
+    "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
+    "b200pt_get_counters",
+]
+
+
+class Texture(ctypes.Structure):
+    """struct texture, texture.h:6-12"""
+    _fields_ = [("Data", ctypes.POINTER(ctypes.c_float)), ("Width", ctypes.c_int32), ("Height", ctypes.c_int32),
+                ("Components", ctypes.c_int32)]
+
+
+class Params(ctypes.Structure):
+    _fields_ = [("struct_size", ctypes.c_int32), ("device", ctypes.c_int32), ("profile", ctypes.c_int32),
+                ("math_mode", ctypes.c_int32), ("num_bounces", ctypes.c_int32), ("env_kind", ctypes.c_int32),
+                ("env_sampler", ctypes.c_int32), ("accum_mode", ctypes.c_int32), ("output_to_screen", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 7)]
+
+
+class Counters(ctypes.Structure):
+    _fields_ = [("paths", ctypes.c_uint64), ("segments", ctypes.c_uint64), ("escapes", ctypes.c_uint64),
+                ("launches", ctypes.c_uint64), ("last_render_ms", ctypes.c_double)]
+
+
+class B200PTError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def load_library():
+    """Loads libb200pt.so; raises if it has not been built (there is no fallback path)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200PTError(f"{LIB_PATH} is missing: run `python -m cpuperformanceraytracer_b200.build` "
+                          "(the CUDA extension is the only implementation)")
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    L.b200pt_api_version.restype = ctypes.c_int
+    L.b200pt_error_string.restype = ctypes.c_char_p
+    L.b200pt_error_string.argtypes = [ctypes.c_int]
+    L.b200pt_last_error.restype = ctypes.c_char_p
+    L.b200pt_last_error.argtypes = [vp]
+    L.b200pt_default_params.argtypes = [ctypes.c_int, ctypes.POINTER(Params)]
+    L.b200pt_create.argtypes = [ctypes.POINTER(Params), ctypes.POINTER(vp)]
+    L.b200pt_destroy.argtypes = [vp]
+    L.b200pt_set_env.argtypes = [vp, Texture]
+    L.b200pt_resize.argtypes = [vp, i32, i32, i32, i32]
+    L.b200pt_reset.argtypes = [vp]
+    L.b200pt_set_frame_counter.argtypes = [vp, i32]
+    L.b200pt_get_frame_counter.argtypes = [vp, ctypes.POINTER(i32)]
+    L.b200pt_render_frames.argtypes = [vp, i32]
+    L.b200pt_synchronize.argtypes = [vp]
+    L.b200pt_upload_target.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.b200pt_download_target.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.b200pt_render_host.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, Texture, vp, i32]
+    L.b200pt_resolve_ldr.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), i32, i32]
+    L.b200pt_bind_device_target.argtypes = [vp, vp]
+    L.b200pt_get_device_target.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
+    L.b200pt_set_stream.argtypes = [vp, vp]
+    L.b200pt_finalize_sum.argtypes = [vp, i32]
+    L.b200pt_download_rng_state.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
+    L.b200pt_get_counters.argtypes = [vp, ctypes.POINTER(Counters)]
+    _lib = L
+    return L
+
+
+def default_params(profile):
+    p = Params()
+    rc = load_library().b200pt_default_params(profile, ctypes.byref(p))
+    if rc != 0:
+        raise B200PTError(f"b200pt_default_params: {load_library().b200pt_error_string(rc).decode()}")
+    return p
+
+
+def _fptr(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+class Renderer:
+    """One rendering context on one GPU = the reference's static render state (frame counter, scene,
+    tile table) plus the HBM-resident accumulation buffer."""
+
+    def __init__(self, profile=PROFILE_V2, math_mode=MATH_PARITY, num_bounces=-1, device=0, env_kind=None,
+                 env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False):
+        self._lib = load_library()
+        self._ctx = ctypes.c_void_p()
+        p = default_params(profile)
+        p.math_mode, p.num_bounces, p.device = math_mode, num_bounces, device
+        p.accum_mode, p.output_to_screen = accum_mode, int(bool(output_to_screen))
+        if env_kind is not None:
+            p.env_kind = env_kind
+        if env_sampler is not None:
+            p.env_sampler = env_sampler
+        self.params = p
+        rc = self._lib.b200pt_create(ctypes.byref(p), ctypes.byref(self._ctx))
+        if rc != 0:
+            self._ctx = ctypes.c_void_p()
+            raise B200PTError(f"b200pt_create failed: {self._lib.b200pt_error_string(rc).decode()} "
+                              "(a B200 is required; there is no CPU fallback)")
+        self.width = self.height = self.ntx = self.nty = 0
+        self._env_keep = None
+
+    # -- plumbing ------------------------------------------------------------------------------
+    def _check(self, rc, what):
+        if rc != 0:
+            raise B200PTError(f"{what}: {self._lib.b200pt_error_string(rc).decode()}: "
+                              f"{self._lib.b200pt_last_error(self._ctx).decode()}")
+
+    def close(self):
+        if self._ctx:
+            self._lib.b200pt_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- reference-shaped operations ---------------------------------------------------------------
+    def set_env(self, env):
+        """env: (H, W, 3) float32, row 0 = bottom (what LoadTexture / LoadCubemapTexture return)."""
+        e = np.ascontiguousarray(env, dtype=np.float32)
+        if e.ndim != 3 or e.shape[2] != 3:
+            raise ValueError("env must be (H, W, 3)")
+        self._env_keep = e
+        t = Texture(_fptr(e), e.shape[1], e.shape[0], 3)
+        self._check(self._lib.b200pt_set_env(self._ctx, t), "b200pt_set_env")
+
+    def resize(self, width, height, ntx, nty):
+        self._check(self._lib.b200pt_resize(self._ctx, width, height, ntx, nty), "b200pt_resize")
+        self.width, self.height, self.ntx, self.nty = width, height, ntx, nty
+
+    def reset(self):
+        self._check(self._lib.b200pt_reset(self._ctx), "b200pt_reset")
+
+    @property
+    def frame_counter(self):
+        v = ctypes.c_int32()
+        self._check(self._lib.b200pt_get_frame_counter(self._ctx, ctypes.byref(v)), "b200pt_get_frame_counter")
+        return v.value
+
+    @frame_counter.setter
+    def frame_counter(self, v):
+        self._check(self._lib.b200pt_set_frame_counter(self._ctx, int(v)), "b200pt_set_frame_counter")
+
+    def render_frames(self, nframes, sync=True):
+        self._check(self._lib.b200pt_render_frames(self._ctx, int(nframes)), "b200pt_render_frames")
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        self._check(self._lib.b200pt_synchronize(self._ctx), "b200pt_synchronize")
+
+    def upload_target(self, buf):
+        b = np.ascontiguousarray(buf, dtype=np.float32).reshape(-1)
+        assert b.size == self.width * self.height * 3
+        self._check(self._lib.b200pt_upload_target(self._ctx, _fptr(b)), "b200pt_upload_target")
+
+    def download_target(self):
+        out = np.empty(self.width * self.height * 3, dtype=np.float32)
+        self._check(self._lib.b200pt_download_target(self._ctx, _fptr(out)), "b200pt_download_target")
+        return out
+
+    def render_host(self, buffer_out, width, height, ntx, nty, nframes, env=None, screen=None):
+        """The reference-facing call (DemofoxRenderOptV4 signature + frame count) on HOST buffers."""
+        assert buffer_out.dtype == np.float32 and buffer_out.flags["C_CONTIGUOUS"]
+        if env is not None:
+            e = env if (env.dtype == np.float32 and env.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(env, np.float32)
+            self._env_keep = e
+            t = Texture(_fptr(e), e.shape[1], e.shape[0], 3)
+        else:
+            t = Texture(None, 0, 0, 3)
+        sp = screen.ctypes.data_as(ctypes.c_void_p) if screen is not None else None
+        rc = self._lib.b200pt_render_host(self._ctx, _fptr(buffer_out), width, height, ntx, nty, width // ntx,
+                                          height // nty, 3, t, sp, int(nframes))
+        self._check(rc, "b200pt_render_host")
+        self.width, self.height, self.ntx, self.nty = width, height, ntx, nty
+
+    def resolve_ldr(self, mode=LDR_FILE_RGBA, bump_frame_counter=False):
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        rc = self._lib.b200pt_resolve_ldr(self._ctx, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), mode,
+                                          int(bump_frame_counter))
+        self._check(rc, "b200pt_resolve_ldr")
+        return out
+
+    def rng_state(self):
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        rc = self._lib.b200pt_download_rng_state(self._ctx, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+        self._check(rc, "b200pt_download_rng_state")
+        return out
+
+    def counters(self):
+        c = Counters()
+        self._check(self._lib.b200pt_get_counters(self._ctx, ctypes.byref(c)), "b200pt_get_counters")
+        return {"paths": c.paths, "segments": c.segments, "escapes": c.escapes, "launches": c.launches,
+                "last_render_ms": c.last_render_ms}
+
+    # -- multi-GPU plumbing ------------------------------------------------------------------------
+    def bind_device_target(self, device_ptr):
+        self._check(self._lib.b200pt_bind_device_target(self._ctx, ctypes.c_void_p(device_ptr)), "b200pt_bind_device_target")
+
+    def device_target(self):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self._check(self._lib.b200pt_get_device_target(self._ctx, ctypes.byref(p), ctypes.byref(n)), "b200pt_get_device_target")
+        return p.value, n.value
+
+    def set_stream(self, cuda_stream_ptr):
+        self._check(self._lib.b200pt_set_stream(self._ctx, ctypes.c_void_p(cuda_stream_ptr)), "b200pt_set_stream")
+
+    def finalize_sum(self, total_frames):
+        self._check(self._lib.b200pt_finalize_sum(self._ctx, int(total_frames)), "b200pt_finalize_sum")
+
+
+def detile(buf, width, height, ntx, nty):
+    """tile-major SoA8 accumulation buffer (RenderTile, v4.cpp:1189-1252) -> (H, W, 3) image."""
+    tw, th = width // ntx, height // nty
+    a = np.asarray(buf, dtype=np.float32).reshape(nty, ntx, th, tw // 8, 3, 8)
+    return np.ascontiguousarray(a.transpose(0, 2, 1, 3, 5, 4).reshape(height, width, 3))

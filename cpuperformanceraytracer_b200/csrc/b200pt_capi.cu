@@ -1,0 +1,560 @@
+// b200pt_capi.cu -- implementation of the C ABI declared in include/b200pt.h.
+// Owns the device state the reference keeps in file-scope statics (frame counter, scene, tile
+// table: demofox_path_tracing_optimization_v4.cpp:34,378,386,1343) plus the HBM copies of the
+// caller's buffers.  No CPU rendering path exists here: without a usable GPU every call fails.
+#include "../../include/b200pt.h"
+
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../host/scene_setup.h"
+#include "pt_common.cuh"
+
+using namespace b200pt;
+
+struct b200pt_context {
+    b200pt_params params{};
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;  // own_stream or a caller-provided one
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+
+    CornellScene cornell{};
+    V4Scene v4{};
+    float cameraDistance = 1.f;
+
+    // target
+    int width = 0, height = 0, ntx = 0, nty = 0, tile_w = 0, tile_h = 0;
+    float* d_target_own = nullptr;
+    float* d_target = nullptr;  // own or bound
+    uint32_t* d_screen = nullptr;
+    uint32_t* d_rng = nullptr;
+    int* d_work_counter = nullptr;
+    DeviceCounters* d_counters = nullptr;
+    float* h_pinned = nullptr;  // staging for render_host (pinned, W*H*3 floats)
+    uint32_t* h_pinned_screen = nullptr;
+    size_t pinned_floats = 0;
+
+    // env
+    float* d_env_rgb = nullptr;
+    float4* d_env_rgba = nullptr;
+    cudaTextureObject_t env_tex = 0;
+    int env_w = 0, env_h = 0;
+    const float* last_env_ptr = nullptr;
+
+    int iframe = 0;
+    int blocks_per_sm = 0;
+    uint64_t paths = 0, launches = 0;
+    double last_render_ms = 0.0;
+    bool timing_pending = false;
+    std::string last_error;
+};
+
+namespace {
+
+int fail(b200pt_context* ctx, int code, const std::string& msg)
+{
+    if (ctx) ctx->last_error = msg;
+    return code;
+}
+
+#define CUDA_TRY(ctx, expr)                                                                         \
+    do {                                                                                            \
+        cudaError_t e_ = (expr);                                                                    \
+        if (e_ != cudaSuccess) {                                                                    \
+            return fail(ctx, e_ == cudaErrorMemoryAllocation ? B200PT_ERR_OUT_OF_MEMORY : B200PT_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
+        }                                                                                           \
+    } while (0)
+
+bool uses_env(const b200pt_params& p)
+{
+    if (p.profile == B200PT_PROFILE_SIMT_TEXTURED) return true;
+    return p.profile == B200PT_PROFILE_OPT_V4 && p.env_kind != B200PT_ENV_NONE;
+}
+
+LaunchConfig launch_config(const b200pt_context* c)
+{
+    LaunchConfig lc{};
+    lc.profile = c->params.profile;
+    lc.env_kind = c->params.profile == B200PT_PROFILE_SIMT_TEXTURED ? kEnvEquirect
+                 : c->params.profile == B200PT_PROFILE_V2           ? kEnvNone
+                                                                    : c->params.env_kind;
+    lc.env_sampler = c->params.profile == B200PT_PROFILE_OPT_V4 && c->params.env_kind != B200PT_ENV_NONE
+                         ? c->params.env_sampler
+                         : kSamplerPoint;
+    lc.accum_mode = c->params.accum_mode;
+    lc.block = 256;
+    lc.grid = 1;
+    return lc;
+}
+
+void free_target(b200pt_context* c)
+{
+    if (c->d_target_own) cudaFree(c->d_target_own);
+    if (c->d_screen) cudaFree(c->d_screen);
+    if (c->d_rng) cudaFree(c->d_rng);
+    if (c->h_pinned) cudaFreeHost(c->h_pinned);
+    if (c->h_pinned_screen) cudaFreeHost(c->h_pinned_screen);
+    c->d_target_own = c->d_target = nullptr;
+    c->d_screen = nullptr;
+    c->d_rng = nullptr;
+    c->h_pinned = nullptr;
+    c->h_pinned_screen = nullptr;
+    c->pinned_floats = 0;
+}
+
+void free_env(b200pt_context* c)
+{
+    if (c->env_tex) cudaDestroyTextureObject(c->env_tex);
+    if (c->d_env_rgb) cudaFree(c->d_env_rgb);
+    if (c->d_env_rgba) cudaFree(c->d_env_rgba);
+    c->env_tex = 0;
+    c->d_env_rgb = nullptr;
+    c->d_env_rgba = nullptr;
+    c->env_w = c->env_h = 0;
+    c->last_env_ptr = nullptr;
+}
+
+int collect_timing(b200pt_context* c)
+{
+    if (c->timing_pending) {
+        float ms = 0.f;
+        CUDA_TRY(c, cudaEventSynchronize(c->ev1));
+        CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        c->last_render_ms = ms;
+        c->timing_pending = false;
+    }
+    return B200PT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int b200pt_api_version(void) { return B200PT_API_VERSION; }
+
+const char* b200pt_error_string(int code)
+{
+    switch (code) {
+    case B200PT_OK: return "ok";
+    case B200PT_ERR_INVALID_ARGUMENT: return "invalid argument";
+    case B200PT_ERR_CUDA: return "CUDA error / no usable device";
+    case B200PT_ERR_NOT_READY: return "not ready (resize / set_env first)";
+    case B200PT_ERR_OUT_OF_MEMORY: return "out of device memory";
+    default: return "unknown error";
+    }
+}
+
+const char* b200pt_last_error(b200pt_context* ctx) { return ctx ? ctx->last_error.c_str() : "null context"; }
+
+int b200pt_default_params(int profile, b200pt_params* p)
+{
+    if (!p || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_OPT_V4) return B200PT_ERR_INVALID_ARGUMENT;
+    std::memset(p, 0, sizeof(*p));
+    p->struct_size = (int32_t)sizeof(b200pt_params);
+    p->device = 0;
+    p->profile = profile;
+    p->math_mode = B200PT_MATH_PARITY;
+    p->num_bounces = -1;
+    p->accum_mode = B200PT_ACCUM_RUNNING_AVERAGE;
+    p->output_to_screen = 0;
+    if (profile == B200PT_PROFILE_OPT_V4) {
+        p->env_kind = B200PT_ENV_EQUIRECT;       // USE_ENV_MAP 1, USE_ENV_CUBEMAP 0
+        p->env_sampler = B200PT_SAMPLER_RANDOM;  // USE_RANDOM_JITTER_TEXTURE_SAMPLING 1
+    } else if (profile == B200PT_PROFILE_SIMT_TEXTURED) {
+        p->env_kind = B200PT_ENV_EQUIRECT;
+        p->env_sampler = B200PT_SAMPLER_POINT;
+    }
+    return B200PT_OK;
+}
+
+int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
+{
+    if (!params || !out_ctx) return B200PT_ERR_INVALID_ARGUMENT;
+    *out_ctx = nullptr;
+    if (params->struct_size != (int32_t)sizeof(b200pt_params)) return B200PT_ERR_INVALID_ARGUMENT;
+    if (params->profile < B200PT_PROFILE_V2 || params->profile > B200PT_PROFILE_OPT_V4) return B200PT_ERR_INVALID_ARGUMENT;
+    if (params->math_mode != B200PT_MATH_PARITY && params->math_mode != B200PT_MATH_FAST) return B200PT_ERR_INVALID_ARGUMENT;
+    if (params->accum_mode != B200PT_ACCUM_RUNNING_AVERAGE && params->accum_mode != B200PT_ACCUM_SUM) return B200PT_ERR_INVALID_ARGUMENT;
+    if (params->profile == B200PT_PROFILE_OPT_V4) {
+        if (params->env_kind < B200PT_ENV_NONE || params->env_kind > B200PT_ENV_CUBEMAP) return B200PT_ERR_INVALID_ARGUMENT;
+        if (params->env_kind != B200PT_ENV_NONE && params->env_sampler != B200PT_SAMPLER_BILINEAR &&
+            params->env_sampler != B200PT_SAMPLER_RANDOM)
+            return B200PT_ERR_INVALID_ARGUMENT;
+    }
+    b200pt_context* c = new (std::nothrow) b200pt_context();
+    if (!c) return B200PT_ERR_OUT_OF_MEMORY;
+    c->params = *params;
+    if (c->params.num_bounces < 0) c->params.num_bounces = (params->profile == B200PT_PROFILE_OPT_V4) ? 8 : 4;
+    c->device = params->device;
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0 || c->device < 0 || c->device >= ndev) {
+        delete c;
+        return B200PT_ERR_CUDA;  // no CPU fallback
+    }
+    cudaDeviceProp prop{};
+    if (cudaSetDevice(c->device) != cudaSuccess || cudaGetDeviceProperties(&prop, c->device) != cudaSuccess ||
+        prop.major < 10) {
+        delete c;
+        return B200PT_ERR_CUDA;  // kernels are sm_100a only
+    }
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaMalloc(&c->d_work_counter, sizeof(int)) != cudaSuccess ||
+        cudaMalloc(&c->d_counters, sizeof(DeviceCounters)) != cudaSuccess ||
+        cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)) != cudaSuccess) {
+        b200pt_destroy(c);
+        return B200PT_ERR_CUDA;
+    }
+    c->stream = c->own_stream;
+
+    // InitializeCamera / InitializeScene (v4.cpp:1403-1502) and the Cornell vertex tables
+    c->cameraDistance = camera_distance();
+    build_cornell_scene(&c->cornell, params->profile == B200PT_PROFILE_SIMT_TEXTURED);
+    build_v4_scene(&c->v4);
+
+    LaunchConfig lc = launch_config(c);
+    int bps = 0;
+    e = (c->params.math_mode == B200PT_MATH_PARITY) ? occupancy_parity(lc, &bps) : occupancy_fast(lc, &bps);
+    if (e != cudaSuccess || bps <= 0) {
+        b200pt_destroy(c);
+        return B200PT_ERR_CUDA;
+    }
+    c->blocks_per_sm = bps;
+    *out_ctx = c;
+    return B200PT_OK;
+}
+
+int b200pt_destroy(b200pt_context* c)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    cudaSetDevice(c->device);
+    if (c->own_stream) cudaStreamSynchronize(c->own_stream);
+    free_target(c);
+    free_env(c);
+    if (c->d_work_counter) cudaFree(c->d_work_counter);
+    if (c->d_counters) cudaFree(c->d_counters);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return B200PT_OK;
+}
+
+int b200pt_set_env(b200pt_context* c, b200pt_texture tex)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!tex.Data || tex.Width <= 0 || tex.Height <= 0 || tex.Components != 3)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "env texture must be RGB f32 with positive size");
+    // the reference indexes texels through binary32 arithmetic (texture.cpp:56-65,84): exact up to 2^24 floats
+    if ((long long)tex.Width * tex.Height * 3 >= (1LL << 24))
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "env texture too large for the reference's float texel indexing");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const size_t texels = (size_t)tex.Width * tex.Height;
+    if (texels != (size_t)c->env_w * c->env_h) {
+        free_env(c);
+        CUDA_TRY(c, cudaMalloc(&c->d_env_rgb, texels * 3 * sizeof(float)));
+        CUDA_TRY(c, cudaMalloc(&c->d_env_rgba, texels * sizeof(float4)));
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeLinear;
+        rd.res.linear.devPtr = c->d_env_rgba;
+        rd.res.linear.desc = cudaCreateChannelDesc<float4>();
+        rd.res.linear.sizeInBytes = texels * sizeof(float4);
+        cudaTextureDesc td{};
+        td.readMode = cudaReadModeElementType;
+        td.filterMode = cudaFilterModePoint;
+        td.addressMode[0] = cudaAddressModeBorder;
+        td.normalizedCoords = 0;
+        CUDA_TRY(c, cudaCreateTextureObject(&c->env_tex, &rd, &td, nullptr));
+    }
+    c->env_w = tex.Width;
+    c->env_h = tex.Height;
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_env_rgb, tex.Data, texels * 3 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, launch_pack_env(c->d_env_rgb, c->d_env_rgba, texels, c->stream));
+    c->launches++;
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    c->last_env_ptr = tex.Data;
+    return B200PT_OK;
+}
+
+int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx, int32_t nty)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    // CheckValidSettings, Application.cpp:36-94
+    if (width <= 0 || height <= 0 || ntx <= 0 || nty <= 0 || width % ntx || height % nty || (width / ntx) % 8)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "invalid tiling: need W % ntx == 0, H % nty == 0, tile width % 8 == 0");
+    if ((long long)width * height * 3 >= (1LL << 31)) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "image too large");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    const size_t nfloats = (size_t)width * height * 3;
+    const bool bound = c->d_target && c->d_target != c->d_target_own;
+    if ((size_t)c->width * c->height != (size_t)width * height || !c->d_target_own) {
+        free_target(c);
+        CUDA_TRY(c, cudaMalloc(&c->d_target_own, nfloats * sizeof(float)));
+        CUDA_TRY(c, cudaMalloc(&c->d_screen, (size_t)width * height * sizeof(uint32_t)));
+        CUDA_TRY(c, cudaMalloc(&c->d_rng, (size_t)width * height * sizeof(uint32_t)));
+        c->d_target = c->d_target_own;
+    } else if (!bound) {
+        c->d_target = c->d_target_own;
+    }
+    c->width = width;
+    c->height = height;
+    c->ntx = ntx;
+    c->nty = nty;
+    c->tile_w = width / ntx;
+    c->tile_h = height / nty;
+    return b200pt_reset(c);
+}
+
+int b200pt_reset(b200pt_context* c)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t nfloats = (size_t)c->width * c->height * 3;
+    CUDA_TRY(c, cudaMemsetAsync(c->d_target, 0, nfloats * sizeof(float), c->stream));  // Application.cpp:151
+    CUDA_TRY(c, cudaMemsetAsync(c->d_screen, 0, (size_t)c->width * c->height * 4, c->stream));
+    CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
+    c->iframe = 0;
+    c->paths = 0;
+    return B200PT_OK;
+}
+
+int b200pt_set_frame_counter(b200pt_context* c, int32_t iframe)
+{
+    if (!c || iframe < 0) return B200PT_ERR_INVALID_ARGUMENT;
+    c->iframe = iframe;
+    return B200PT_OK;
+}
+
+int b200pt_get_frame_counter(b200pt_context* c, int32_t* iframe)
+{
+    if (!c || !iframe) return B200PT_ERR_INVALID_ARGUMENT;
+    *iframe = c->iframe;
+    return B200PT_OK;
+}
+
+int b200pt_render_frames(b200pt_context* c, int32_t nframes)
+{
+    if (!c || nframes < 0) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    if (uses_env(c->params) && !c->env_tex) return fail(c, B200PT_ERR_NOT_READY, "this profile samples an env map: set_env first");
+    if (nframes == 0) return B200PT_OK;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
+
+    RenderParams rp{};
+    rp.target = c->d_target;
+    rp.rng_out = c->d_rng;
+    rp.work_counter = c->d_work_counter;
+    rp.counters = c->d_counters;
+    rp.env = c->env_tex;
+    rp.env_w = c->env_w;
+    rp.env_h = c->env_h;
+    rp.width = c->width;
+    rp.height = c->height;
+    rp.tile_w = c->tile_w;
+    rp.tile_h = c->tile_h;
+    rp.num_tiles_x = c->ntx;
+    rp.groups_per_tile_row = c->tile_w / 8;
+    rp.groups_per_tile = rp.groups_per_tile_row * c->tile_h;
+    rp.num_groups = c->width * c->height / 8;
+    rp.num_items = (rp.num_groups + 3) / 4;
+    rp.first_frame = c->iframe + 1;  // iFrame += 1 before the render, v4.cpp:1703
+    rp.nframes = nframes;
+    rp.num_bounces = c->params.num_bounces;
+    rp.cameraDistance = c->cameraDistance;
+
+    LaunchConfig lc = launch_config(c);
+    // persistent grid: every SM holds blocks_per_sm resident CTAs; warps pull 32-pixel items
+    const int warps_per_block = lc.block / 32;
+    const int max_useful_blocks = (rp.num_items + warps_per_block - 1) / warps_per_block;
+    lc.grid = c->sm_count * c->blocks_per_sm;
+    if (lc.grid > max_useful_blocks) lc.grid = max_useful_blocks;
+    if (lc.grid < 1) lc.grid = 1;
+
+    CUDA_TRY(c, cudaMemsetAsync(c->d_work_counter, 0, sizeof(int), c->stream));
+    CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    cudaError_t e = (c->params.math_mode == B200PT_MATH_PARITY)
+                        ? launch_render_parity(lc, rp, c->cornell, c->v4, c->stream)
+                        : launch_render_fast(lc, rp, c->cornell, c->v4, c->stream);
+    CUDA_TRY(c, e);
+    CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
+    c->timing_pending = true;
+    c->launches++;
+    c->iframe += nframes;
+    c->paths += (uint64_t)c->width * c->height * (uint64_t)nframes;
+
+    if (c->params.output_to_screen) {  // OUTPUT_TO_SCREEN: per-render tone map, v4.cpp:1562-1564
+        CUDA_TRY(c, launch_resolve_ldr(c->d_target, c->d_screen, c->width, c->height, c->tile_w, c->tile_h, c->ntx,
+                                       B200PT_LDR_SCREEN_BGRA, c->stream));
+        c->launches++;
+    }
+    return B200PT_OK;
+}
+
+int b200pt_synchronize(b200pt_context* c)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return collect_timing(c);
+}
+
+int b200pt_upload_target(b200pt_context* c, const float* host_src)
+{
+    if (!c || !host_src) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_target, host_src, (size_t)c->width * c->height * 3 * sizeof(float),
+                                cudaMemcpyHostToDevice, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+int b200pt_download_target(b200pt_context* c, float* host_dst)
+{
+    if (!c || !host_dst) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_target, (size_t)c->width * c->height * 3 * sizeof(float),
+                                cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return collect_timing(c);
+}
+
+int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H, int32_t NumTilesX, int32_t NumTilesY,
+                       int32_t TileWidth, int32_t TileHeight, int32_t NumChannels, b200pt_texture Texture,
+                       void* ScreenBufferData, int32_t nframes)
+{
+    if (!c || !BufferOut || nframes < 0) return B200PT_ERR_INVALID_ARGUMENT;
+    if (NumChannels != 3) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "NumChannels must be 3");
+    if (NumTilesX <= 0 || NumTilesY <= 0 || TileWidth * NumTilesX != W || TileHeight * NumTilesY != H)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "tiles must cover the buffer exactly");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    if (c->width != W || c->height != H || c->ntx != NumTilesX || c->nty != NumTilesY) {
+        const int keep_frame = c->iframe;
+        int rc = b200pt_resize(c, W, H, NumTilesX, NumTilesY);
+        if (rc != B200PT_OK) return rc;
+        c->iframe = keep_frame;  // the reference's static iFrame survives a resize
+    }
+    if (uses_env(c->params)) {
+        if (Texture.Data && (Texture.Data != c->last_env_ptr || Texture.Width != c->env_w || Texture.Height != c->env_h)) {
+            int rc = b200pt_set_env(c, Texture);
+            if (rc != B200PT_OK) return rc;
+        }
+    }
+    const size_t nfloats = (size_t)W * H * 3;
+    if (c->pinned_floats != nfloats) {
+        if (c->h_pinned) cudaFreeHost(c->h_pinned);
+        if (c->h_pinned_screen) cudaFreeHost(c->h_pinned_screen);
+        c->h_pinned = nullptr;
+        c->h_pinned_screen = nullptr;
+        CUDA_TRY(c, cudaMallocHost(&c->h_pinned, nfloats * sizeof(float)));
+        CUDA_TRY(c, cudaMallocHost(&c->h_pinned_screen, (size_t)W * H * sizeof(uint32_t)));
+        c->pinned_floats = nfloats;
+    }
+    // host accumulation state -> pinned staging -> HBM; render; HBM -> pinned -> host
+    std::memcpy(c->h_pinned, BufferOut, nfloats * sizeof(float));
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_target, c->h_pinned, nfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    int rc = b200pt_render_frames(c, nframes);
+    if (rc != B200PT_OK) return rc;
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_pinned, c->d_target, nfloats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    const bool want_screen = ScreenBufferData && c->params.output_to_screen;
+    if (want_screen)
+        CUDA_TRY(c, cudaMemcpyAsync(c->h_pinned_screen, c->d_screen, (size_t)W * H * sizeof(uint32_t),
+                                    cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    std::memcpy(BufferOut, c->h_pinned, nfloats * sizeof(float));
+    if (want_screen) std::memcpy(ScreenBufferData, c->h_pinned_screen, (size_t)W * H * sizeof(uint32_t));
+    return collect_timing(c);
+}
+
+int b200pt_resolve_ldr(b200pt_context* c, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter)
+{
+    if (!c || !host_dst || (mode != B200PT_LDR_FILE_RGBA && mode != B200PT_LDR_SCREEN_BGRA)) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, launch_resolve_ldr(c->d_target, c->d_screen, c->width, c->height, c->tile_w, c->tile_h, c->ntx, mode, c->stream));
+    c->launches++;
+    CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_screen, (size_t)c->width * c->height * sizeof(uint32_t),
+                                cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (bump_frame_counter) c->iframe += 1;  // CopyOutputToFile: iFrame += 1.0f, v4.cpp:1741
+    return B200PT_OK;
+}
+
+int b200pt_bind_device_target(b200pt_context* c, void* device_ptr)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target_own) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    c->d_target = device_ptr ? static_cast<float*>(device_ptr) : c->d_target_own;
+    return B200PT_OK;
+}
+
+int b200pt_get_device_target(b200pt_context* c, void** device_ptr, size_t* bytes)
+{
+    if (!c || !device_ptr) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    *device_ptr = c->d_target;
+    if (bytes) *bytes = (size_t)c->width * c->height * 3 * sizeof(float);
+    return B200PT_OK;
+}
+
+int b200pt_set_stream(b200pt_context* c, void* cuda_stream)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
+    c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return B200PT_OK;
+}
+
+int b200pt_finalize_sum(b200pt_context* c, int32_t total_frames)
+{
+    if (!c || total_frames < 0) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const float scale = 1.0f / ((float)total_frames + 1.f);
+    CUDA_TRY(c, launch_scale(c->d_target, (size_t)c->width * c->height * 3, scale, c->stream));
+    c->launches++;
+    return B200PT_OK;
+}
+
+int b200pt_download_rng_state(b200pt_context* c, uint32_t* host_dst)
+{
+    if (!c || !host_dst) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_rng) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_rng, (size_t)c->width * c->height * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                c->stream));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+int b200pt_get_counters(b200pt_context* c, b200pt_counters* out)
+{
+    if (!c || !out) return B200PT_ERR_INVALID_ARGUMENT;
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
+    DeviceCounters dc{};
+    CUDA_TRY(c, cudaMemcpy(&dc, c->d_counters, sizeof(dc), cudaMemcpyDeviceToHost));
+    out->paths = c->paths;
+    out->segments = dc.segments;
+    out->escapes = dc.escapes;
+    out->launches = c->launches;
+    out->last_render_ms = c->last_render_ms;
+    return B200PT_OK;
+}
+
+}  // extern "C"

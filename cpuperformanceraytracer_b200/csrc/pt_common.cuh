@@ -1,0 +1,104 @@
+// pt_common.cuh -- shared types of the B200 path-tracing kernels (host + device).
+// Reference paths are relative to /root/reference/CPUPerformanceRayTracer/.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace b200pt {
+
+struct v3 {
+    float x, y, z;
+};
+
+// ---- scene tables, filled on the host (host/scene_setup.cpp) with the reference's own
+// ---- float expressions and handed to the kernel as a __grid_constant__ parameter ------------
+
+// Cornell box of demofox_path_tracing_v2.cpp:320-454 / ..._simt_textured.cpp:278-385.
+// `n` is normalize(cross(c - a, c - b)), the per-ray expression of v2.cpp:166 hoisted to the
+// host: it only depends on the vertices, so the hoist is bit-neutral.
+struct LegacyQuad {
+    v3 a, b, c, d, n;
+};
+struct LegacyMaterial {
+    v3 albedo, emissive, specularColor;
+    float percentSpecular, roughness;
+};
+constexpr int kCornellQuads = 6;
+constexpr int kCornellSpheres = 3;
+constexpr int kCornellObjects = kCornellQuads + kCornellSpheres;
+struct CornellScene {
+    LegacyQuad quad[kCornellQuads];
+    float4 sphere[kCornellSpheres];  // xyz + radius
+    LegacyMaterial mat[kCornellObjects];
+};
+
+// Scene of ..._optimization_v4.cpp:1403-1496 with PrecomputeQuadData (:269-319).
+struct V4Quad {
+    v3 V0, NxV01, NxV20, NxV02, NxV30, n;
+};
+struct V4Material {
+    v3 albedo, emissive, specularColor, refractionColor;
+    float specularChance, specularRoughness, IOR, refractionChance, refractionRoughness;
+};
+constexpr int kV4Quads = 4;
+constexpr int kV4Spheres = 7;
+constexpr int kV4Objects = kV4Quads + kV4Spheres;
+struct V4Scene {
+    V4Quad quad[kV4Quads];
+    float4 sphere[kV4Spheres];
+    V4Material mat[kV4Objects];
+    v3 cameraPosition;
+    float cameraDistance;
+};
+
+struct DeviceCounters {
+    unsigned long long segments;
+    unsigned long long escapes;
+};
+
+// One launch = `nframes` consecutive render calls of the reference over the whole image.
+struct RenderParams {
+    float* target;        // tile-major SoA8 accumulation buffer (RenderTile, v4.cpp:1189-1252)
+    uint32_t* rng_out;    // optional: final RNG state per pixel, row-major (debug/parity)
+    int* work_counter;    // atomic work-item counter: replaces work_queue.cpp's ring + CAS pop
+    DeviceCounters* counters;
+    cudaTextureObject_t env;  // RGBA32F linear texture, texel t = reference float index 3t
+    int env_w, env_h;
+    int width, height;
+    int tile_w, tile_h, num_tiles_x;
+    int groups_per_tile_row;  // tile_w / 8
+    int groups_per_tile;      // tile_w / 8 * tile_h
+    int num_groups;           // width * height / 8
+    int num_items;            // ceil(num_groups / 4): one warp = 4 groups = 32 pixels
+    int first_frame;          // 1-based iFrame of the first render call in this launch
+    int nframes;
+    int num_bounces;
+    float cameraDistance;     // 1 / tan(FOV/2), computed on the host like v2.cpp:546
+};
+
+enum : int { kProfileV2 = 0, kProfileSimtTextured = 1, kProfileV4 = 2 };
+enum : int { kEnvNone = 0, kEnvEquirect = 1, kEnvCubemap = 2 };
+enum : int { kSamplerPoint = 0, kSamplerBilinear = 1, kSamplerRandom = 2 };
+enum : int { kAccumAverage = 0, kAccumSum = 1 };
+
+struct LaunchConfig {
+    int profile, env_kind, env_sampler, accum_mode;
+    int grid, block;
+};
+
+// implemented in pt_kernels_parity.cu / pt_kernels_fast.cu
+cudaError_t launch_render_parity(const LaunchConfig& lc, const RenderParams& rp, const CornellScene& cs,
+                                 const V4Scene& vs, cudaStream_t stream);
+cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const CornellScene& cs,
+                               const V4Scene& vs, cudaStream_t stream);
+cudaError_t occupancy_parity(const LaunchConfig& lc, int* blocks_per_sm);
+cudaError_t occupancy_fast(const LaunchConfig& lc, int* blocks_per_sm);
+
+// pt_post.cu
+cudaError_t launch_resolve_ldr(const float* target, uint32_t* out, int width, int height, int tile_w, int tile_h,
+                               int num_tiles_x, int mode, cudaStream_t stream);
+cudaError_t launch_scale(float* target, size_t n, float scale, cudaStream_t stream);
+cudaError_t launch_pack_env(const float* rgb, float4* rgba, size_t texels, cudaStream_t stream);
+
+}  // namespace b200pt

@@ -1,0 +1,136 @@
+// scene_setup.cpp -- host-side construction of the scene tables the kernel reads.
+//
+// The reference builds its scenes at start-up with AVX2 float arithmetic
+// (InitializeScene / PrecomputeQuadData / InitializeCamera,
+// demofox_path_tracing_optimization_v4.cpp:269-319,1403-1502) or re-evaluates constant vertex
+// expressions per ray (demofox_path_tracing_v2.cpp:320-454).  The same binary32 expressions are
+// evaluated here once, on the host, in the same order, so the tables hold the same bits.
+// Compile with -ffp-contract=off; fused operations are spelled std::fmaf where the reference's
+// dot()/cross() fuse (mathlib.h:144-146, 770-778).
+#include "scene_setup.h"
+
+#include <cmath>
+#include <cstring>
+
+namespace b200pt {
+namespace {
+
+inline v3 mk(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+inline v3 add(v3 u, v3 v) { return mk(u.x + v.x, u.y + v.y, u.z + v.z); }
+inline v3 sub(v3 u, v3 v) { return mk(u.x - v.x, u.y - v.y, u.z - v.z); }
+inline v3 muls(v3 u, float c) { return mk(u.x * c, u.y * c, u.z * c); }
+inline v3 divs(v3 u, float c) { return mk(u.x / c, u.y / c, u.z / c); }
+inline v3 neg(v3 u) { return mk(-u.x, -u.y, -u.z); }
+inline float dot(v3 u, v3 v) { return std::fmaf(u.x, v.x, std::fmaf(u.y, v.y, u.z * v.z)); }
+inline v3 cross(v3 u, v3 v)
+{
+    return mk(std::fmaf(u.y, v.z, -(u.z * v.y)), std::fmaf(u.z, v.x, -(u.x * v.z)), std::fmaf(u.x, v.y, -(u.y * v.x)));
+}
+inline v3 normalize(v3 v) { return muls(v, 1.0f / std::sqrt(dot(v, v))); }
+
+}  // namespace
+
+float camera_distance()
+{
+    const float c_FOVDegrees = 90.0f;
+    const float c_pi = 3.14159265359f;
+    return 1.0f / std::tan(c_FOVDegrees * 0.5f * c_pi / 180.0f);  // v2.cpp:546, v4.cpp:1500
+}
+
+void build_cornell_scene(CornellScene* s, bool simt_textured_materials)
+{
+    std::memset(s, 0, sizeof(*s));
+    const v3 T = mk(0.0f, 0.0f, 10.0f);  // sceneTranslation, v2.cpp:323
+    static const float Q[kCornellQuads][4][3] = {
+        {{-12.6f, -12.6f, 25.0f}, {12.6f, -12.6f, 25.0f}, {12.6f, 12.6f, 25.0f}, {-12.6f, 12.6f, 25.0f}},        // back wall  :328-331
+        {{-12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 15.0f}, {-12.6f, -12.45f, 15.0f}},  // floor      :345-348
+        {{-12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 15.0f}, {-12.6f, 12.5f, 15.0f}},          // ceiling    :362-365
+        {{-12.5f, -12.6f, 25.0f}, {-12.5f, -12.6f, 15.0f}, {-12.5f, 12.6f, 15.0f}, {-12.5f, 12.6f, 25.0f}},      // left wall  :379-382
+        {{12.5f, -12.6f, 25.0f}, {12.5f, -12.6f, 15.0f}, {12.5f, 12.6f, 15.0f}, {12.5f, 12.6f, 25.0f}},          // right wall :396-399
+        {{-5.0f, 12.4f, 22.5f}, {5.0f, 12.4f, 22.5f}, {5.0f, 12.4f, 17.5f}, {-5.0f, 12.4f, 17.5f}}};             // light      :413-416
+    for (int i = 0; i < kCornellQuads; i++) {
+        LegacyQuad& q = s->quad[i];
+        q.a = add(mk(Q[i][0][0], Q[i][0][1], Q[i][0][2]), T);
+        q.b = add(mk(Q[i][1][0], Q[i][1][1], Q[i][1][2]), T);
+        q.c = add(mk(Q[i][2][0], Q[i][2][1], Q[i][2][2]), T);
+        q.d = add(mk(Q[i][3][0], Q[i][3][1], Q[i][3][2]), T);
+        q.n = normalize(cross(sub(q.c, q.a), sub(q.c, q.b)));  // v2.cpp:166
+    }
+    static const float SX[kCornellSpheres] = {-9.0f, 0.0f, 9.0f};  // v2.cpp:429,438,447
+    for (int i = 0; i < kCornellSpheres; i++) {
+        const v3 c = add(mk(SX[i], -9.5f, 20.0f), T);
+        s->sphere[i] = make_float4(c.x, c.y, c.z, 3.0f + 0.0f);
+    }
+    LegacyMaterial* m = s->mat;
+    m[0].albedo = mk(0.7f, 0.7f, 0.7f);
+    m[1].albedo = mk(0.7f, 0.7f, 0.7f);
+    m[2].albedo = mk(0.7f, 0.7f, 0.7f);
+    m[3].albedo = mk(0.7f, 0.1f, 0.1f);
+    m[4].albedo = mk(0.1f, 0.7f, 0.1f);
+    m[5].emissive = muls(mk(1.0f, 0.9f, 0.7f), 20.0f);
+    if (!simt_textured_materials) {  // v2.cpp:430-452
+        m[6].albedo = mk(0.9f, 0.9f, 0.5f); m[6].percentSpecular = 0.1f; m[6].roughness = 0.2f; m[6].specularColor = mk(0.9f, 0.9f, 0.9f);
+        m[7].albedo = mk(0.9f, 0.5f, 0.9f); m[7].percentSpecular = 0.3f; m[7].roughness = 0.2f; m[7].specularColor = mk(0.9f, 0.9f, 0.9f);
+        m[8].albedo = mk(0.f, 0.f, 1.f);    m[8].percentSpecular = 0.5f; m[8].roughness = 0.4f; m[8].specularColor = mk(1.f, 0.f, 0.f);
+    } else {  // simt_textured.cpp:370-383
+        m[6].albedo = mk(0.9f, 0.9f, 0.75f);
+        m[7].albedo = mk(0.9f, 0.75f, 0.9f);
+        m[8].albedo = mk(0.9f, 0.75f, 0.9f);
+    }
+}
+
+// PrecomputeQuadData, v4.cpp:269-319
+static void precompute_quad(V4Quad* q, v3 V0, v3 V1, v3 V2, v3 V3)
+{
+    const v3 V01 = sub(V1, V0), V02 = sub(V2, V0), V30 = sub(V0, V3);
+    const v3 V20 = neg(V02);
+    const v3 V01xV02 = cross(V01, V02);
+    const v3 V02xV03 = cross(V30, V01);
+    const v3 N = normalize(V01xV02);
+    const float DetTop = dot(V02xV03, N);
+    const float DetBot = dot(V01xV02, N);
+    q->V0 = V0;
+    q->n = N;
+    q->NxV01 = divs(cross(N, V01), DetBot);
+    q->NxV20 = divs(cross(N, V20), DetBot);
+    q->NxV02 = divs(cross(N, V02), DetTop);
+    q->NxV30 = divs(cross(N, V30), DetTop);
+}
+
+void build_v4_scene(V4Scene* s)
+{
+    std::memset(s, 0, sizeof(*s));
+    const v3 T = mk(0.0f, 0.0f, 10.0f);  // v4.cpp:1407
+    precompute_quad(&s->quad[0], add(mk(-25.0f, -12.5f, 5.0f), T), add(mk(25.0f, -12.5f, 5.0f), T),
+                    add(mk(25.0f, -12.5f, -5.0f), T), add(mk(-25.0f, -12.5f, -5.0f), T));           // floor :1416-1419
+    precompute_quad(&s->quad[1], mk(-25.0f, -1.5f, 5.0f), mk(25.0f, -1.5f, 5.0f), mk(25.0f, -10.5f, 5.0f),
+                    mk(-25.0f, -10.5f, 5.0f));                                                       // backdrop, untranslated :1430-1433
+    precompute_quad(&s->quad[2], add(mk(-7.5f, 12.5f, 5.0f), T), add(mk(7.5f, 12.5f, 5.0f), T),
+                    add(mk(7.5f, 12.5f, -5.0f), T), add(mk(-7.5f, 12.5f, -5.0f), T));               // ceiling :1447-1450
+    precompute_quad(&s->quad[3], add(mk(-5.0f, 12.4f, 2.5f), T), add(mk(5.0f, 12.4f, 2.5f), T),
+                    add(mk(5.0f, 12.4f, -2.5f), T), add(mk(-5.0f, 12.4f, -2.5f), T));               // light :1461-1464
+    // AddMaterialToScene copies albedo.x into all three channels (v4.cpp:1370-1372): preserved
+    s->mat[0].albedo = mk(0.7f, 0.7f, 0.7f);
+    s->mat[1].albedo = mk(.35f, .35f, .35f);
+    s->mat[2].albedo = mk(0.7f, 0.7f, 0.7f);
+    s->mat[3].emissive = muls(mk(1.0f, 0.9f, 0.7f), 20.0f);
+    const int c_numSpheres = kV4Spheres;
+    for (int i = 0; i < c_numSpheres; i++) {  // v4.cpp:1474-1495
+        const v3 c = add(mk(-18.0f + 6.0f * (float)i, -8.0f, 0.0f), T);
+        s->sphere[i] = make_float4(c.x, c.y, c.z, 2.8f + 0.0f);
+        V4Material& m = s->mat[kV4Quads + i];
+        const float r = (((float)i) / (float)(c_numSpheres - 1)) * 0.5f;
+        m.specularChance = 0.02f;
+        m.IOR = 1.1f;
+        m.refractionChance = 1.0f;
+        m.albedo = mk(0.9f, 0.9f, 0.9f);
+        m.refractionColor = mk(0.0f, 0.5f, 1.0f);
+        m.specularColor = muls(mk(1.0f, 1.0f, 1.0f), 0.8f);
+        m.specularRoughness = r;
+        m.refractionRoughness = r;
+    }
+    s->cameraDistance = camera_distance();
+    s->cameraPosition = mk(0.f, 0.f, 1.f * 40.f);  // v4.cpp:1501
+}
+
+}  // namespace b200pt

@@ -1,0 +1,179 @@
+/*
+ * b200pt.h -- C ABI of the B200 path-tracing engine (libb200pt.so).
+ *
+ * This is the drop-in boundary for ONE hot path of torgeiba/CPUPerformanceRayTracer: the
+ * per-pixel demofox path loop + env lookup + running-average accumulation that the reference
+ * runs behind its render entry points.  Plain pointers and sizes only; no C++ or torch types.
+ * Every entry point cites the reference interface it replaces (paths relative to
+ * /root/reference/CPUPerformanceRayTracer/).  The C++ overloads with the reference's exact
+ * names/signatures live in cpuperformanceraytracer_b200/host/demofox_render.h and forward here.
+ *
+ * There is no CPU fallback: every call that needs the GPU fails with B200PT_ERR_CUDA when no
+ * sm_100 device is usable.
+ */
+#ifndef B200PT_H
+#define B200PT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200PT_API_VERSION 1
+
+typedef struct b200pt_context b200pt_context;
+
+/* return codes (the reference's entry points are void and __debugbreak() on bad tiling,
+ * Application.cpp:36-94; here every call reports) */
+enum {
+    B200PT_OK = 0,
+    B200PT_ERR_INVALID_ARGUMENT = 1, /* null pointer, bad enum, tiling that CheckValidSettings rejects */
+    B200PT_ERR_CUDA = 2,             /* CUDA runtime error or no usable device */
+    B200PT_ERR_NOT_READY = 3,        /* render before resize / env-using profile without env */
+    B200PT_ERR_OUT_OF_MEMORY = 4
+};
+
+/* which reference renderer's semantics the kernel reproduces */
+enum {
+    B200PT_PROFILE_V2 = 0,            /* DemofoxRenderV2, demofox_path_tracing_v2.cpp:654 (Cornell box,
+                                         diffuse/emissive/specular, jitter, constant ambient) */
+    B200PT_PROFILE_SIMT_TEXTURED = 1, /* DemofoxRenderSimtTextured, ..._simt_textured.cpp:560 (Cornell,
+                                         diffuse/emissive, equirect point-sampled env) */
+    B200PT_PROFILE_OPT_V4 = 2         /* DemofoxRenderOptV4, ..._optimization_v4.cpp:1696 (7 spheres,
+                                         Fresnel/refraction/absorption, equirect or cubemap env) */
+};
+
+/* arithmetic policy */
+enum {
+    B200PT_MATH_PARITY = 0, /* IEEE div/sqrt, fused ops only where the reference writes fmadd/fmsub/
+                               fnmadd, portable sin/cos/atan2/asin: bit-exact against the oracle */
+    B200PT_MATH_FAST = 1    /* FMA contraction + MUFU approximations; same RNG streams and control
+                               flow, ULP-level differences (tolerances in tests/test_gpu_parity.py) */
+};
+
+/* global_preprocessor_flags.h:56-57 USE_ENV_MAP / USE_ENV_CUBEMAP */
+enum { B200PT_ENV_NONE = 0, B200PT_ENV_EQUIRECT = 1, B200PT_ENV_CUBEMAP = 2 };
+/* texture.cpp:101 (point), :164/:275 (bilinear), :186/:341 (random jitter,
+ * global_preprocessor_flags.h:66 USE_RANDOM_JITTER_TEXTURE_SAMPLING) */
+enum { B200PT_SAMPLER_POINT = 0, B200PT_SAMPLER_BILINEAR = 1, B200PT_SAMPLER_RANDOM = 2 };
+
+/* how frames are folded into the f32 target */
+enum {
+    B200PT_ACCUM_RUNNING_AVERAGE = 0, /* reference semantics: avg += (c - avg) / (iFrame + 1),
+                                         ..._optimization_v4.cpp:1200,1239 / ..._v2.cpp:623 */
+    B200PT_ACCUM_SUM = 1              /* target += c; used by spp-sharded multi-GPU renders, followed by
+                                         a sum-reduce and b200pt_finalize_sum() */
+};
+
+/* ScreenBufferData packing, ..._optimization_v4.cpp:1285-1290 (screen) / :1321-1325 (file) */
+enum { B200PT_LDR_FILE_RGBA = 0, B200PT_LDR_SCREEN_BGRA = 1 };
+
+/* mirrors struct texture, texture.h:6-12 (row-major RGB f32, row 0 = bottom after stbi's flip) */
+typedef struct b200pt_texture {
+    const float* Data;
+    int32_t Width;
+    int32_t Height;
+    int32_t Components; /* must be 3 */
+} b200pt_texture;
+
+typedef struct b200pt_params {
+    int32_t struct_size;  /* sizeof(b200pt_params), for ABI evolution */
+    int32_t device;       /* CUDA device ordinal */
+    int32_t profile;      /* B200PT_PROFILE_* */
+    int32_t math_mode;    /* B200PT_MATH_* */
+    int32_t num_bounces;  /* c_numBounces (v2.cpp:22 = 4, v4.cpp:23 = 8); <0 = profile default */
+    int32_t env_kind;     /* OPT_V4 only: B200PT_ENV_* (SIMT_TEXTURED always equirect/point) */
+    int32_t env_sampler;  /* OPT_V4 only: B200PT_SAMPLER_BILINEAR or _RANDOM */
+    int32_t accum_mode;   /* B200PT_ACCUM_* */
+    int32_t output_to_screen; /* OUTPUT_TO_SCREEN (global_preprocessor_flags.h:58): tone-map into the
+                                 screen buffer after every render call */
+    int32_t reserved[7];
+} b200pt_params;
+
+typedef struct b200pt_counters {
+    uint64_t paths;     /* (pixel, frame) samples traced since create/reset */
+    uint64_t segments;  /* scene traces executed by live paths */
+    uint64_t escapes;   /* paths that ended on a miss (one env lookup each) */
+    uint64_t launches;  /* CUDA kernels launched by this library on this context */
+    double last_render_ms; /* device time of the last b200pt_render_frames, CUDA events */
+} b200pt_counters;
+
+/* Fills *p with the reference's checked-in defaults for `profile`
+ * (global_preprocessor_flags.h:56-66, Appendix B of SURVEY.md). */
+int b200pt_default_params(int profile, b200pt_params* p);
+
+/* InitializeGlobalRenderResources (..._optimization_v4.cpp:1640-1661): camera, scene tables;
+ * the thread pool it spawns is replaced by the persistent kernel's atomic work counter. */
+int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx);
+int b200pt_destroy(b200pt_context* ctx);
+
+/* Uploads the environment texture once (the reference re-passes `texture Texture` by value on
+ * every render call, ..._optimization_v4.cpp:1696-1699).  Cubemaps are the W x 6H atlas that
+ * LoadCubemapTexture builds (asset_loading.cpp:18-44). */
+int b200pt_set_env(b200pt_context* ctx, b200pt_texture tex);
+
+/* win32_offscreen_buffer::Resize + ReinitializeRenderTileData (Application.cpp:104-155,
+ * ..._optimization_v4.cpp:1723-1726): (re)allocates the zeroed W*H*3 f32 target and the W*H u32
+ * screen buffer in HBM and fixes the tile geometry.  Same validity rules as CheckValidSettings
+ * (Application.cpp:36-94): W % ntx == 0, H % nty == 0, tile width % 8 == 0. */
+int b200pt_resize(b200pt_context* ctx, int32_t width, int32_t height, int32_t num_tiles_x, int32_t num_tiles_y);
+
+/* zero the target and the frame counter (the state a fresh Resize leaves behind) */
+int b200pt_reset(b200pt_context* ctx);
+
+/* static f32 iFrame (..._optimization_v4.cpp:34): number of render calls made so far */
+int b200pt_set_frame_counter(b200pt_context* ctx, int32_t iframe);
+int b200pt_get_frame_counter(b200pt_context* ctx, int32_t* iframe);
+
+/* == nframes consecutive calls of DemofoxRenderOptV4 / DemofoxRenderV2 / DemofoxRenderSimtTextured
+ * on the device-resident target: iFrame += 1, render every tile, fold into the target.
+ * Asynchronous on the context's stream. */
+int b200pt_render_frames(b200pt_context* ctx, int32_t nframes);
+int b200pt_synchronize(b200pt_context* ctx);
+
+/* copies of the f32 accumulation buffer in the reference's tile-major SoA8 layout
+ * (RenderTile, ..._optimization_v4.cpp:1189-1252); W*H*3 floats */
+int b200pt_upload_target(b200pt_context* ctx, const float* host_src);
+int b200pt_download_target(b200pt_context* ctx, float* host_dst);
+
+/* The reference-facing call: same arguments as DemofoxRenderOptV4
+ * (demofox_path_tracing_optimization_v4.h:14-17) plus a frame count.  BufferOut is the caller's
+ * HOST accumulation buffer (persists across calls); it is copied to the device, nframes are
+ * rendered, and it is copied back, all inside the call.  Texture is uploaded when its pointer or
+ * shape changed since the last call.  ScreenBufferData (may be NULL) receives the tone-mapped
+ * u32 image when output_to_screen is set.  Blocks until done, like the reference. */
+int b200pt_render_host(b200pt_context* ctx, float* BufferOut, int32_t BufferWidth, int32_t BufferHeight,
+                       int32_t NumTilesX, int32_t NumTilesY, int32_t TileWidth, int32_t TileHeight,
+                       int32_t NumChannels, b200pt_texture Texture, void* ScreenBufferData, int32_t nframes);
+
+/* CopyOutputToFile / OutputToScreen (..._optimization_v4.cpp:1260-1331, :1729-1760):
+ * ACES + sRGB + 8-bit pack of the device target into a row-major host u32[W*H].
+ * Like the reference's CopyOutputToFile it also bumps the frame counter when
+ * bump_frame_counter != 0 (..._optimization_v4.cpp:1741). */
+int b200pt_resolve_ldr(b200pt_context* ctx, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter);
+
+/* multi-GPU plumbing: render into / reduce over a caller-owned device buffer (e.g. the storage of
+ * a tensor handed to an NCCL all-reduce).  Pass NULL to go back to the internal buffer. */
+int b200pt_bind_device_target(b200pt_context* ctx, void* device_ptr);
+int b200pt_get_device_target(b200pt_context* ctx, void** device_ptr, size_t* bytes);
+/* launch on a caller-owned cudaStream_t (NULL = the context's own stream) */
+int b200pt_set_stream(b200pt_context* ctx, void* cuda_stream);
+/* ACCUM_SUM epilogue: target *= 1/(total_frames + 1), the value the reference's running average
+ * converges to after total_frames render calls on a zeroed buffer */
+int b200pt_finalize_sum(b200pt_context* ctx, int32_t total_frames);
+
+/* debug/parity hook: u32 RNG state of every pixel after the last rendered frame's path ended
+ * (row-major W*H, row 0 = top); checks wang_hash stream parity bit for bit */
+int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
+
+int b200pt_get_counters(b200pt_context* ctx, b200pt_counters* out);
+const char* b200pt_last_error(b200pt_context* ctx);
+const char* b200pt_error_string(int code);
+int b200pt_api_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
