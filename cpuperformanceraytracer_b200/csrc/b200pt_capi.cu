@@ -322,9 +322,7 @@ int b200pt_reset(b200pt_context* c)
     const size_t nfloats = (size_t)c->width * c->height * 3;
     CUDA_TRY(c, cudaMemsetAsync(c->d_target, 0, nfloats * sizeof(float), c->stream));  // Application.cpp:151
     CUDA_TRY(c, cudaMemsetAsync(c->d_screen, 0, (size_t)c->width * c->height * 4, c->stream));
-    CUDA_TRY(c, cudaMemsetAsync(c->d_counters, 0, sizeof(DeviceCounters), c->stream));
-    c->iframe = 0;
-    c->paths = 0;
+    c->iframe = 0;  // counters stay cumulative since create
     return B200PT_OK;
 }
 

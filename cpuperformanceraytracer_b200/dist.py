@@ -1,0 +1,102 @@
+"""dist.py -- multi-GPU sharding of the path loop (one process per GPU, torch.distributed for the
+plumbing; NCCL over NVLink on GPUs, gloo in the CPU tests of the host logic).
+
+The reference has no distributed code.  Its path loop shards trivially: every (pixel, frame)
+sample re-seeds its RNG from (x, y, iFrame) (demofox_path_tracing_optimization_v4.cpp:1096-1101),
+so frames are independent streams and only the accumulation couples them.
+
+  spp-shard  rank r renders a contiguous block of the 1-based frame range into a SUM buffer
+             (B200PT_ACCUM_SUM); one all-reduce(sum) of the W*H*3 f32 buffer; then every rank
+             scales by 1/(N+1) (b200pt_finalize_sum) -- the value the reference's running average
+             reaches after N calls on a zeroed buffer.  Same samples, different summation order:
+             agrees with the sequential render to ~1e-6 relative (tests), not bit for bit.
+  tile-shard rank r renders tile rows [a, b) of every frame; the buffer is band-major (a row of
+             tiles is contiguous, RenderTile v4.cpp:1189-1194) so each rank owns one contiguous
+             span and an all-gather reassembles the image with no repacking.  Bit-identical to the
+             single-GPU render.
+"""
+from dataclasses import dataclass
+
+
+@dataclass(frozen=True)
+class FrameShard:
+    first_frame: int  # 1-based iFrame of the first render call of this rank
+    nframes: int
+
+
+def shard_frames(total_frames: int, world_size: int, rank: int, first_frame: int = 1) -> FrameShard:
+    """Contiguous, near-equal blocks of the frame range [first_frame, first_frame + total_frames)."""
+    if world_size <= 0 or not (0 <= rank < world_size) or total_frames < 0:
+        raise ValueError("bad shard request")
+    base, rem = divmod(total_frames, world_size)
+    n = base + (1 if rank < rem else 0)
+    start = first_frame + rank * base + min(rank, rem)
+    return FrameShard(start, n)
+
+
+@dataclass(frozen=True)
+class TileRowShard:
+    first_tile_row: int
+    num_tile_rows: int
+    float_offset: int  # offset of the rank's span in the accumulation buffer
+    float_count: int
+
+
+def shard_tile_rows(width: int, height: int, num_tiles_y: int, world_size: int, rank: int) -> TileRowShard:
+    """Tile-row bands: one contiguous span of the band-major buffer per rank."""
+    if height % num_tiles_y or world_size <= 0 or not (0 <= rank < world_size):
+        raise ValueError("bad shard request")
+    base, rem = divmod(num_tiles_y, world_size)
+    n = base + (1 if rank < rem else 0)
+    start = rank * base + min(rank, rem)
+    band = (height // num_tiles_y) * width * 3
+    return TileRowShard(start, n, start * band, n * band)
+
+
+def finalize_scale(total_frames: int) -> float:
+    """1/(N+1): the reference's running average on a zeroed buffer is biased by design
+    (iFrame starts at 1 and the blend factor is 1/(iFrame+1))."""
+    return 1.0 / (float(total_frames) + 1.0)
+
+
+def reduce_sum_(tensor, group=None):
+    """All-reduce(sum) of a rank's SUM buffer in place (NCCL on CUDA tensors, gloo on CPU tensors)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(tensor, op=dist.ReduceOp.SUM, group=group)
+    return tensor
+
+
+class SppShardedRenderer:
+    """spp-sharded render of one image on this rank's GPU.  The accumulation buffer is a torch CUDA
+    tensor (so NCCL can reduce it in place) bound to the engine through b200pt_bind_device_target;
+    kernels run on torch's current stream."""
+
+    def __init__(self, renderer_factory, width, height, ntx, nty, rank, world_size, device):
+        import torch
+        from . import api
+        self.torch = torch
+        self.rank, self.world = rank, world_size
+        self.device = torch.device("cuda", device)
+        self.r = renderer_factory(accum_mode=api.ACCUM_SUM, device=device)
+        self.r.resize(width, height, ntx, nty)
+        self.buf = torch.zeros(width * height * 3, dtype=torch.float32, device=self.device)
+        self.r.bind_device_target(self.buf.data_ptr())
+        # a dedicated (non-default) stream shared by the kernels, the memset and the collective
+        self.stream = torch.cuda.Stream(self.device)
+        self.r.set_stream(self.stream.cuda_stream)
+        torch.cuda.synchronize(self.device)
+
+    def render(self, total_frames, first_frame=1):
+        """Zeroes the buffer, renders this rank's frame block, reduces, scales.  Asynchronous."""
+        sh = shard_frames(total_frames, self.world, self.rank, first_frame)
+        with self.torch.cuda.stream(self.stream):
+            self.buf.zero_()
+            self.r.frame_counter = sh.first_frame - 1
+            self.r.render_frames(sh.nframes, sync=False)
+            reduce_sum_(self.buf)
+            self.r.finalize_sum(total_frames)
+        return self.buf
+
+    def close(self):
+        self.r.close()

@@ -93,7 +93,7 @@ typedef struct b200pt_params {
 } b200pt_params;
 
 typedef struct b200pt_counters {
-    uint64_t paths;     /* (pixel, frame) samples traced since create/reset */
+    uint64_t paths;     /* (pixel, frame) samples traced since create */
     uint64_t segments;  /* scene traces executed by live paths */
     uint64_t escapes;   /* paths that ended on a miss (one env lookup each) */
     uint64_t launches;  /* CUDA kernels launched by this library on this context */

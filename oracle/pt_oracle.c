@@ -876,3 +876,20 @@ int oracle_resolve_ldr(const float* target, int W, int H, int ntx, int nty, uint
         }
     return 0;
 }
+
+/* ---- test hooks for oracle/portable_math.h -------------------------------------------------- */
+void oracle_pm_sincosf(float a, float* s, float* c) { pm_sincosf(a, s, c); }
+float oracle_pm_atan2f(float y, float x) { return pm_atan2f(y, x); }
+float oracle_pm_asinf(float x) { return pm_asinf(x); }
+void oracle_pm_sincosf_array(const float* a, float* s, float* c, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) pm_sincosf(a[i], &s[i], &c[i]);
+}
+void oracle_pm_atan2f_array(const float* y, const float* x, float* out, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = pm_atan2f(y[i], x[i]);
+}
+void oracle_pm_asinf_array(const float* x, float* out, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = pm_asinf(x[i]);
+}

@@ -1,0 +1,200 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+Bars:
+  * B200PT_MATH_PARITY: BIT-EXACT f32 accumulation buffers, RNG states and segment counters.
+  * B200PT_MATH_FAST (FMA contraction + MUFU approximations, same RNG streams): tolerances stated
+    per test (RMSE over the f32 buffer at matched seeds/spp).
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_cases, load_golden, stats
+
+pytestmark = pytest.mark.gpu
+
+from cpuperformanceraytracer_b200 import api  # noqa: E402
+
+GPU_PROFILE = {0: api.PROFILE_V2, 1: api.PROFILE_SIMT_TEXTURED, 2: api.PROFILE_OPT_V4}
+
+
+def make_renderer(case_profile, bounces, env_kind, env_sampler, math_mode=api.MATH_PARITY, **kw):
+    gp = GPU_PROFILE[case_profile]
+    if gp == api.PROFILE_OPT_V4:
+        return api.Renderer(profile=gp, math_mode=math_mode, num_bounces=bounces, env_kind=env_kind,
+                            env_sampler=env_sampler, **kw)
+    return api.Renderer(profile=gp, math_mode=math_mode, num_bounces=bounces, **kw)
+
+
+@pytest.mark.parametrize("case", golden_cases(), ids=lambda c: c["name"])
+def test_parity_mode_reproduces_reference_golden(oracle, case):
+    """GPU vs buffers produced by the reference's own code (tests/golden)."""
+    g = load_golden(case["name"])
+    env = oracle.synthetic_env(*case["env_shape"]) if case["env_shape"] else None
+    with make_renderer(case["profile"], case["bounces"], case["env_kind"], case["env_sampler"]) as r:
+        if env is not None:
+            r.set_env(env)
+        r.resize(case["width"], case["height"], case["ntx"], case["nty"])
+        r.render_frames(case["frames"])
+        assert np.array_equal(r.download_target(), g["buffer"])
+        r.render_frames(case["continued_frames"])
+        assert np.array_equal(r.download_target(), g["continued"])
+        assert r.frame_counter == case["frames"] + case["continued_frames"]
+
+
+CONFIGS = [
+    ("v2", 0, None, 0, 0, 8),
+    ("simt_textured", 1, (256, 128), 1, 0, 4),
+    ("v4_equirect_random", 2, (256, 128), 1, 2, 8),
+    ("v4_equirect_bilinear", 2, (256, 128), 1, 1, 8),
+    ("v4_cubemap_random", 2, (64, 384), 2, 2, 8),
+    ("v4_cubemap_bilinear", 2, (64, 384), 2, 1, 8),
+    ("v4_no_env", 2, None, 0, 0, 8),
+]
+
+
+@pytest.mark.parametrize("name,profile,envshape,ek,es,bounces", CONFIGS, ids=[c[0] for c in CONFIGS])
+def test_parity_mode_bit_exact_vs_oracle(oracle, name, profile, envshape, ek, es, bounces):
+    """Seeded 256x192, 12 frames: buffer, per-pixel RNG state after the last path, counters."""
+    W, H, ntx, nty, frames = 256, 192, 4, 6, 12
+    env = oracle.synthetic_env(*envshape) if envshape else None
+    o, oc = oracle.render(profile, W, H, ntx, nty, bounces, frames, env=env, env_kind=ek, env_sampler=es)
+    with make_renderer(profile, bounces, ek, es) as r:
+        if env is not None:
+            r.set_env(env)
+        r.resize(W, H, ntx, nty)
+        r.render_frames(frames)
+        g = r.download_target()
+        assert np.array_equal(g, o), "max abs %g rmse %g" % stats(g, o)
+        c = r.counters()
+        assert (c["paths"], c["segments"], c["escapes"]) == (oc["paths"], oc["segments"], oc["escapes"])
+        # wang_hash stream parity: state of a sample of pixels after frame `frames`
+        rs = r.rng_state()
+        p, keep = oracle.make_params(profile, W, H, ntx, nty, bounces, env, ek, es)
+        import ctypes
+        rng = np.random.default_rng(3)
+        for _ in range(300):
+            x, y = int(rng.integers(W)), int(rng.integers(H))
+            assert int(rs[y, x]) == oracle.lib().oracle_final_rng_state(ctypes.byref(p), x, y, frames)
+
+
+@pytest.mark.parametrize("name,profile,envshape,ek,es,bounces,tol", [
+    # FMA contraction + MUFU rcp/rsqrt/sqrt/sincos: ULP-level perturbations, rare branch flips.
+    # RMSE over the f32 buffer at 64 spp; env textures here are per-texel noise, the worst case for
+    # the point/jitter samplers (a 1-ulp direction change can pick the neighbouring texel).
+    ("v2", 0, None, 0, 0, 8, 2e-3),
+    ("v4_equirect_bilinear", 2, (256, 128), 1, 1, 8, 2e-3),
+    ("v4_cubemap_random", 2, (64, 384), 2, 2, 8, 2e-3),
+], ids=["v2", "v4_equirect_bilinear", "v4_cubemap_random"])
+def test_fast_mode_within_tolerance(oracle, name, profile, envshape, ek, es, bounces, tol):
+    W, H, ntx, nty, frames = 256, 192, 4, 6, 64
+    env = oracle.synthetic_env(*envshape) if envshape else None
+    o, oc = oracle.render(profile, W, H, ntx, nty, bounces, frames, env=env, env_kind=ek, env_sampler=es)
+    with make_renderer(profile, bounces, ek, es, math_mode=api.MATH_FAST) as r:
+        if env is not None:
+            r.set_env(env)
+        r.resize(W, H, ntx, nty)
+        r.render_frames(frames)
+        g = r.download_target()
+    mx, rmse = stats(g, o)
+    assert np.isfinite(g).all()
+    assert rmse <= tol, (mx, rmse)
+    assert abs(float(g.mean()) - float(o.mean())) <= 1e-3 * float(o.mean())
+
+
+def test_frame_chunking_and_tiling_invariance(oracle):
+    """16 frames in one launch == 5 + 11 frames in two launches == any tile grid (bit-exact)."""
+    W, H = 192, 96
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=8) as r:
+        r.resize(W, H, 2, 4)
+        r.render_frames(16)
+        a = api.detile(r.download_target(), W, H, 2, 4)
+        r.resize(W, H, 6, 3)
+        r.render_frames(5)
+        r.render_frames(11)
+        b = api.detile(r.download_target(), W, H, 6, 3)
+    assert np.array_equal(a, b)
+
+
+def test_render_host_is_the_reference_call(oracle):
+    """b200pt_render_host == DemofoxRenderOptV4 called nframes times on the caller's host buffer."""
+    W, H, ntx, nty = 128, 72, 4, 6
+    env = oracle.synthetic_env(128, 64)
+    o, _ = oracle.render(oracle.PROFILE_V4, W, H, ntx, nty, 8, 5, env=env, env_kind=1, env_sampler=2)
+    buf = np.zeros(W * H * 3, dtype=np.float32)
+    with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=8) as r:
+        r.render_host(buf, W, H, ntx, nty, 2, env=env)
+        r.render_host(buf, W, H, ntx, nty, 3, env=env)
+    assert np.array_equal(buf, o)
+
+
+def test_ldr_resolve_bit_exact(oracle):
+    g = load_golden("v4_ldr")
+    with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=8, output_to_screen=True) as r:
+        r.set_env(oracle.synthetic_env(128, 64))
+        r.resize(128, 72, 4, 6)
+        r.upload_target(g["buffer"])
+        assert np.array_equal(r.resolve_ldr(api.LDR_FILE_RGBA), g["ldr"])
+        assert np.array_equal(r.resolve_ldr(api.LDR_SCREEN_BGRA), oracle.resolve_ldr(g["buffer"], 128, 72, 4, 6, mode=1))
+        f0 = r.frame_counter
+        r.resolve_ldr(api.LDR_FILE_RGBA, bump_frame_counter=True)  # CopyOutputToFile bumps iFrame, v4.cpp:1741
+        assert r.frame_counter == f0 + 1
+        # OUTPUT_TO_SCREEN path of render_host
+        buf = np.zeros(128 * 72 * 3, dtype=np.float32)
+        scr = np.zeros((72, 128), dtype=np.uint32)
+        r.frame_counter = 0
+        r.render_host(buf, 128, 72, 4, 6, 6, screen=scr)
+        assert np.array_equal(buf, g["buffer"])
+        assert np.array_equal(scr, oracle.resolve_ldr(buf, 128, 72, 4, 6, mode=1))
+
+
+def test_sum_mode_matches_running_average(oracle):
+    """ACCUM_SUM + finalize (the spp-shard epilogue) vs the sequential running average: different
+    rounding order only; tolerance 2e-6 relative to the image scale (documented in DESIGN.md)."""
+    W, H, frames = 128, 96, 32
+    o, _ = oracle.render(oracle.PROFILE_V2, W, H, 2, 4, 8, frames)
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=8, accum_mode=api.ACCUM_SUM) as r:
+        r.resize(W, H, 2, 4)
+        r.render_frames(10)
+        r.render_frames(22)
+        r.finalize_sum(frames)
+        g = r.download_target()
+    assert np.allclose(g, o, rtol=2e-6, atol=2e-6)
+
+
+def test_edge_cases(oracle):
+    # smallest legal image (one SoA8 group), ragged warp (groups not a multiple of 4), bounces = 0
+    for (W, H, ntx, nty, b) in [(8, 1, 1, 1, 4), (24, 5, 3, 5, 4), (40, 3, 1, 3, 0), (8, 8, 1, 8, 16)]:
+        o, _ = oracle.render(oracle.PROFILE_V2, W, H, ntx, nty, b, 3)
+        with api.Renderer(profile=api.PROFILE_V2, num_bounces=b) as r:
+            r.resize(W, H, ntx, nty)
+            r.render_frames(0)
+            r.render_frames(3)
+            assert np.array_equal(r.download_target(), o)
+
+
+def test_error_behaviour():
+    with api.Renderer(profile=api.PROFILE_SIMT_TEXTURED) as r:
+        with pytest.raises(api.B200PTError, match="invalid tiling"):
+            r.resize(60, 32, 2, 2)  # tile width 30: CheckValidSettings would __debugbreak
+        with pytest.raises(api.B200PTError):
+            r.render_frames(1)  # before resize
+        r.resize(64, 32, 2, 2)
+        with pytest.raises(api.B200PTError, match="env"):
+            r.render_frames(1)  # env-sampling profile without env
+
+
+def test_full_size_properties():
+    """BASELINE config 2 size (1920x1080, 8 bounces): determinism and chunk invariance, bit-exact;
+    path accounting."""
+    W, H = 1920, 1080
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=8) as r:
+        r.resize(W, H, 10, 15)
+        r.render_frames(8)
+        a = r.download_target()
+        c = r.counters()
+        assert c["paths"] == W * H * 8 and c["paths"] <= c["segments"] <= 9 * c["paths"]
+        r.reset()
+        r.render_frames(3)
+        r.render_frames(5)
+        b = r.download_target()
+    assert np.array_equal(a, b) and np.isfinite(a).all() and a.min() >= 0

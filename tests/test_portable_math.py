@@ -1,0 +1,66 @@
+"""oracle/portable_math.h defines sin/cos/atan2/asin for the oracle (MSVC SVML is closed source:
+'parity unpinned' at that boundary).  Check the definitions are faithful: <= 1 ulp from the
+platform libm and equal to the correctly rounded float64-evaluated value on sampled inputs."""
+import ctypes
+
+import numpy as np
+
+
+def _ulp_diff(a, b):
+    ia = a.view(np.int32).astype(np.int64)
+    ib = b.view(np.int32).astype(np.int64)
+    ia = np.where(ia < 0, -(ia & 0x7FFFFFFF), ia)
+    ib = np.where(ib < 0, -(ib & 0x7FFFFFFF), ib)
+    return np.abs(ia - ib)
+
+
+def _fp(a):
+    return a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+def test_sincos(oracle):
+    rng = np.random.default_rng(1)
+    # the hot path's domain: a = u * (2*pi) with u = k / 2^31 (v2.cpp:79-83)
+    k = rng.integers(0, 2 ** 31, size=2_000_000, dtype=np.int64)
+    u = k.astype(np.int32).astype(np.float32) / np.float32(2147483648.0)
+    a = (u * np.float32(2.0 * np.float32(3.14159265359))).astype(np.float32)
+    s = np.empty_like(a)
+    c = np.empty_like(a)
+    oracle.lib().oracle_pm_sincosf_array(_fp(a), _fp(s), _fp(c), a.size)
+    s64, c64 = np.sin(a.astype(np.float64)).astype(np.float32), np.cos(a.astype(np.float64)).astype(np.float32)
+    assert _ulp_diff(s, s64).max() <= 1 and (s == s64).mean() > 0.9999
+    assert _ulp_diff(c, c64).max() <= 1 and (c == c64).mean() > 0.9999
+    assert _ulp_diff(s, np.sin(a)).max() <= 1 and _ulp_diff(c, np.cos(a)).max() <= 1
+    # exact landmarks
+    for ang, es, ec in [(0.0, 0.0, 1.0)]:
+        ss, cc = ctypes.c_float(), ctypes.c_float()
+        oracle.lib().oracle_pm_sincosf(ctypes.c_float(ang), ctypes.byref(ss), ctypes.byref(cc))
+        assert ss.value == es and cc.value == ec
+
+
+def test_atan2_asin(oracle):
+    rng = np.random.default_rng(2)
+    x = rng.uniform(-1, 1, 1_000_000).astype(np.float32)
+    y = rng.uniform(-1, 1, 1_000_000).astype(np.float32)
+    out = np.empty_like(x)
+    oracle.lib().oracle_pm_atan2f_array(_fp(y), _fp(x), _fp(out), x.size)
+    ref = np.arctan2(y.astype(np.float64), x.astype(np.float64)).astype(np.float32)
+    assert _ulp_diff(out, ref).max() <= 1 and (out == ref).mean() > 0.9999
+    oracle.lib().oracle_pm_asinf_array(_fp(x), _fp(out), x.size)
+    ref = np.arcsin(x.astype(np.float64)).astype(np.float32)
+    assert _ulp_diff(out, ref).max() <= 1 and (out == ref).mean() > 0.9999
+
+
+def test_edge_cases(oracle):
+    L = oracle.lib()
+    L.oracle_pm_atan2f.restype = ctypes.c_float
+    L.oracle_pm_atan2f.argtypes = [ctypes.c_float, ctypes.c_float]
+    L.oracle_pm_asinf.restype = ctypes.c_float
+    L.oracle_pm_asinf.argtypes = [ctypes.c_float]
+    pi = np.float32(np.pi)
+    assert L.oracle_pm_atan2f(0.0, -1.0) == pi
+    assert L.oracle_pm_atan2f(-0.0, -1.0) == -pi
+    assert L.oracle_pm_atan2f(0.0, 0.0) == 0.0
+    assert L.oracle_pm_atan2f(1.0, 0.0) == np.float32(np.pi / 2)
+    assert np.isnan(L.oracle_pm_asinf(1.0000001))  # normalised directions can overshoot 1 by an ulp
+    assert L.oracle_pm_asinf(-1.0) == -np.float32(np.pi / 2)
