@@ -1,0 +1,172 @@
+// demofox_render.cpp -- see demofox_render.h.
+#include "demofox_render.h"
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+
+#include "b200pt.h"
+#include "image_io.h"
+
+namespace {
+
+B200RenderOptions g_options;
+b200pt_context* g_ctx[3] = {nullptr, nullptr, nullptr};  // one per reference translation unit
+bool g_tile_data_changed = true;                         // tileDataChanged, v4.cpp:1348
+
+[[noreturn]] void die(const char* what, b200pt_context* ctx, int rc)
+{
+    std::fprintf(stderr, "b200pt: %s failed: %s%s%s\n", what, b200pt_error_string(rc), ctx ? ": " : "",
+                 ctx ? b200pt_last_error(ctx) : "");
+    std::abort();  // the reference __debugbreak()s on invalid settings (Application.cpp:50-91)
+}
+
+b200pt_context* context_for(int profile)
+{
+    if (g_ctx[profile]) return g_ctx[profile];
+    b200pt_params p;
+    int rc = b200pt_default_params(profile, &p);
+    if (rc != B200PT_OK) die("b200pt_default_params", nullptr, rc);
+    p.device = g_options.device;
+    p.math_mode = g_options.math_mode;
+    p.num_bounces = (profile == B200PT_PROFILE_OPT_V4) ? g_options.v4_num_bounces : g_options.v2_num_bounces;
+    if (profile == B200PT_PROFILE_OPT_V4) {
+        p.env_kind = !g_options.use_env_map ? B200PT_ENV_NONE : (g_options.use_env_cubemap ? B200PT_ENV_CUBEMAP : B200PT_ENV_EQUIRECT);
+        p.env_sampler = g_options.use_random_jitter_texture_sampling ? B200PT_SAMPLER_RANDOM : B200PT_SAMPLER_BILINEAR;
+        p.output_to_screen = g_options.output_to_screen;
+    }
+    rc = b200pt_create(&p, &g_ctx[profile]);
+    if (rc != B200PT_OK) die("b200pt_create (a B200 is required; there is no CPU fallback)", nullptr, rc);
+    return g_ctx[profile];
+}
+
+void render(int profile, f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture,
+            void* ScreenBufferData, i32 NumFrames)
+{
+    b200pt_context* ctx = context_for(profile);
+    b200pt_texture t;
+    t.Data = Texture.Data;
+    t.Width = Texture.Width;
+    t.Height = Texture.Height;
+    t.Components = Texture.Components;
+    const int rc = b200pt_render_host(ctx, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, t, ScreenBufferData, NumFrames);
+    if (rc != B200PT_OK) die("b200pt_render_host", ctx, rc);
+    g_tile_data_changed = false;
+}
+
+}  // namespace
+
+void B200SetRenderOptions(const B200RenderOptions& options) { g_options = options; }
+
+void InitializeGlobalRenderResources() { context_for(B200PT_PROFILE_OPT_V4); }
+
+void ReinitializeRenderTileData() { g_tile_data_changed = true; }  // geometry is re-derived from every call's arguments
+
+void DemofoxRenderOptV4(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture,
+                        void* ScreenBufferData)
+{
+    render(B200PT_PROFILE_OPT_V4, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, ScreenBufferData, 1);
+}
+
+void DemofoxRenderOptV4Frames(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture,
+                              void* ScreenBufferData, i32 NumFrames)
+{
+    render(B200PT_PROFILE_OPT_V4, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, ScreenBufferData, NumFrames);
+}
+
+void DemofoxRenderV2(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture)
+{
+    render(B200PT_PROFILE_V2, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, 1);
+}
+
+void DemofoxRenderV2Frames(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture,
+                           i32 NumFrames)
+{
+    render(B200PT_PROFILE_V2, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, NumFrames);
+}
+
+void DemofoxRenderSimtTextured(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture)
+{
+    render(B200PT_PROFILE_SIMT_TEXTURED, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, 1);
+}
+
+void DemofoxRenderSimtTexturedFrames(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels,
+                                     texture Texture, i32 NumFrames)
+{
+    render(B200PT_PROFILE_SIMT_TEXTURED, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, NumFrames);
+}
+
+// CopyOutputToFile (v4.cpp:1729-1760): tone-maps the f32 buffer into ScreenBufferData
+// (A=FF | B<<16 | G<<8 | R, row-major) and, like the reference, bumps the frame counter.
+void CopyOutputToFile(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture, void* ScreenBufferData)
+{
+    b200pt_context* ctx = context_for(B200PT_PROFILE_OPT_V4);
+    if (NumChannels != 3 || TW * NTX != W || TH * NTY != H) die("CopyOutputToFile (tiling)", ctx, B200PT_ERR_INVALID_ARGUMENT);
+    int32_t frame = 0;
+    b200pt_get_frame_counter(ctx, &frame);
+    int rc = b200pt_resize(ctx, W, H, NTX, NTY);  // no-op reallocation when the size is unchanged; zeroes, so re-upload
+    if (rc != B200PT_OK) die("b200pt_resize", ctx, rc);
+    b200pt_set_frame_counter(ctx, frame);
+    rc = b200pt_upload_target(ctx, BufferOut);
+    if (rc != B200PT_OK) die("b200pt_upload_target", ctx, rc);
+    rc = b200pt_resolve_ldr(ctx, static_cast<uint32_t*>(ScreenBufferData), B200PT_LDR_FILE_RGBA, 1);
+    if (rc != B200PT_OK) die("b200pt_resolve_ldr", ctx, rc);
+}
+
+texture LoadTexture(char* filename)
+{
+    texture t;
+    b200pt::HostImage img;
+    std::string err;
+    if (!b200pt::LoadRadianceHDR(filename, &img, &err)) {
+        std::fprintf(stderr, "LoadTexture(%s): %s\n", filename, err.c_str());
+        return t;  // Data == 0, like a failed stbi_loadf
+    }
+    t.Data = static_cast<f32*>(std::malloc(img.rgb.size() * sizeof(f32)));
+    std::memcpy(t.Data, img.rgb.data(), img.rgb.size() * sizeof(f32));
+    t.Width = img.width;
+    t.Height = img.height;
+    t.Components = 3;
+    return t;
+}
+
+texture LoadCubemapTexture(char* filename[6])
+{
+    texture t;
+    b200pt::HostImage img;
+    std::string err, paths[6];
+    for (int i = 0; i < 6; i++) paths[i] = filename[i];
+    if (!b200pt::LoadCubemapAtlas(paths, &img, &err)) {
+        std::fprintf(stderr, "LoadCubemapTexture: %s\n", err.c_str());
+        return t;
+    }
+    t.Data = static_cast<f32*>(std::malloc(img.rgb.size() * sizeof(f32)));
+    std::memcpy(t.Data, img.rgb.data(), img.rgb.size() * sizeof(f32));
+    t.Width = img.width;
+    t.Height = img.height;
+    t.Components = 3;
+    return t;
+}
+
+void WriteImage(char* filename, i32 width, i32 height, i32 components, void* data)
+{
+    std::string err;
+    if (components != 4 || !b200pt::WriteBMP32(filename, width, height, static_cast<const uint32_t*>(data), &err))
+        std::fprintf(stderr, "WriteImage(%s): %s\n", filename, components != 4 ? "only 4-component buffers are supported" : err.c_str());
+}
+
+B200RenderStats B200GetRenderStats(int variant)
+{
+    B200RenderStats s{};
+    if (variant < 0 || variant > 2 || !g_ctx[variant]) return s;
+    b200pt_counters c;
+    if (b200pt_get_counters(g_ctx[variant], &c) == B200PT_OK) {
+        s.last_render_ms = c.last_render_ms;
+        s.paths = c.paths;
+        s.segments = c.segments;
+        s.escapes = c.escapes;
+        s.launches = c.launches;
+    }
+    return s;
+}

@@ -1,0 +1,83 @@
+// demofox_render.h -- the reference's render entry points, by name and signature, on top of the
+// C ABI (include/b200pt.h).  A caller written against the reference
+// (ApplicationState::Render / RenderOffline / PostprocessAndWriteImageToFile,
+// Application.cpp:381-477) compiles unchanged against this header and links libdemofox_b200.so.
+//
+//   reference declaration                                  file:line
+//   DemofoxRenderOptV4 / CopyOutputToFile /
+//   InitializeGlobalRenderResources /
+//   ReinitializeRenderTileData                             demofox_path_tracing_optimization_v4.h:14-26
+//   DemofoxRenderV2                                        demofox_path_tracing_v2.h:8-10
+//   DemofoxRenderSimtTextured                              demofox_path_tracing_simt_textured.h:8-10
+//   struct texture                                         texture.h:6-12
+//   LoadTexture / LoadCubemapTexture / WriteImage          asset_loading.h
+//
+// Like the reference, the entry points keep their state in file-scope statics (frame counter,
+// scene, tile table), are not re-entrant, block until the frame is done, and report nothing: a
+// failure (no GPU, invalid tiling) prints the reason and aborts, where the reference would
+// __debugbreak() (Application.cpp:50-91).
+#pragma once
+#include <cstdint>
+
+#include "global_preprocessor_flags.h"
+
+typedef uint8_t u8;
+typedef uint32_t u32;
+typedef uint64_t u64;
+typedef int32_t i32;
+typedef float f32;
+typedef double f64;
+
+struct texture {
+    f32* Data = 0;
+    i32 Width = 0;
+    i32 Height = 0;
+    i32 Components = 3;
+};
+
+// runtime counterparts of the reference's compile-time switches; defaults come from the macros
+struct B200RenderOptions {
+    int device = 0;
+    int math_mode = 0;            // 0 = parity (bit-exact vs the oracle), 1 = fast
+    int v2_num_bounces = 4;       // c_numBounces, demofox_path_tracing_v2.cpp:22
+    int v4_num_bounces = 8;       // c_numBounces, demofox_path_tracing_optimization_v4.cpp:23
+    int use_env_map = USE_ENV_MAP;
+    int use_env_cubemap = USE_ENV_CUBEMAP;
+    int use_random_jitter_texture_sampling = USE_RANDOM_JITTER_TEXTURE_SAMPLING;
+    int output_to_screen = OUTPUT_TO_SCREEN;
+};
+// must be called before the first render call of a variant (the contexts are created lazily)
+void B200SetRenderOptions(const B200RenderOptions& options);
+
+// ---- the reference's entry points ----------------------------------------------------------------
+void DemofoxRenderOptV4(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                        i32 TileHeight, i32 NumChannels, texture Texture, void* ScreenBufferData);
+void CopyOutputToFile(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                      i32 TileHeight, i32 NumChannels, texture Texture, void* ScreenBufferData);
+void InitializeGlobalRenderResources();
+void ReinitializeRenderTileData();
+void DemofoxRenderV2(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                     i32 TileHeight, i32 NumChannels, texture Texture);
+void DemofoxRenderSimtTextured(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                               i32 TileHeight, i32 NumChannels, texture Texture);
+
+// ---- batched forms: NumFrames consecutive calls of the entry point above in ONE kernel launch and
+// ---- one host<->device round trip (what RenderOffline's frame loop amounts to, Application.cpp:426-438)
+void DemofoxRenderOptV4Frames(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                              i32 TileHeight, i32 NumChannels, texture Texture, void* ScreenBufferData, i32 NumFrames);
+void DemofoxRenderV2Frames(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                           i32 TileHeight, i32 NumChannels, texture Texture, i32 NumFrames);
+void DemofoxRenderSimtTexturedFrames(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY,
+                                     i32 TileWidth, i32 TileHeight, i32 NumChannels, texture Texture, i32 NumFrames);
+
+// ---- asset_loading.h ---------------------------------------------------------------------------------
+texture LoadTexture(char* filename);
+texture LoadCubemapTexture(char* filename[6]);
+void WriteImage(char* filename, i32 width, i32 height, i32 components, void* data);
+
+// device time of the last render call in ms (CUDA events), paths/segments since start-up
+struct B200RenderStats {
+    double last_render_ms;
+    u64 paths, segments, escapes, launches;
+};
+B200RenderStats B200GetRenderStats(int variant /*0 = v2, 1 = simt_textured, 2 = opt_v4*/);

@@ -81,9 +81,9 @@ def test_parity_mode_bit_exact_vs_oracle(oracle, name, profile, envshape, ek, es
     # FMA contraction + MUFU rcp/rsqrt/sqrt/sincos: ULP-level perturbations, rare branch flips.
     # RMSE over the f32 buffer at 64 spp; env textures here are per-texel noise, the worst case for
     # the point/jitter samplers (a 1-ulp direction change can pick the neighbouring texel).
-    ("v2", 0, None, 0, 0, 8, 2e-3),
-    ("v4_equirect_bilinear", 2, (256, 128), 1, 1, 8, 2e-3),
-    ("v4_cubemap_random", 2, (64, 384), 2, 2, 8, 2e-3),
+    ("v2", 0, None, 0, 0, 8, 3e-3),
+    ("v4_equirect_bilinear", 2, (256, 128), 1, 1, 8, 3e-3),
+    ("v4_cubemap_random", 2, (64, 384), 2, 2, 8, 3e-3),
 ], ids=["v2", "v4_equirect_bilinear", "v4_cubemap_random"])
 def test_fast_mode_within_tolerance(oracle, name, profile, envshape, ek, es, bounces, tol):
     W, H, ntx, nty, frames = 256, 192, 4, 6, 64
