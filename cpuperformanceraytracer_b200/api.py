@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters",
+    "b200pt_get_counters", "b200pt_compute_cull_rects",
 ]
 
 
@@ -41,7 +41,7 @@ class Params(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_int32), ("device", ctypes.c_int32), ("profile", ctypes.c_int32),
                 ("math_mode", ctypes.c_int32), ("num_bounces", ctypes.c_int32), ("env_kind", ctypes.c_int32),
                 ("env_sampler", ctypes.c_int32), ("accum_mode", ctypes.c_int32), ("output_to_screen", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 7)]
+                ("disable_camera_culling", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6)]
 
 
 class Counters(ctypes.Structure):
@@ -91,6 +91,7 @@ def load_library():
     L.b200pt_finalize_sum.argtypes = [vp, i32]
     L.b200pt_download_rng_state.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.b200pt_get_counters.argtypes = [vp, ctypes.POINTER(Counters)]
+    L.b200pt_compute_cull_rects.argtypes = [ctypes.c_int, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     _lib = L
     return L
 
@@ -112,12 +113,14 @@ class Renderer:
     tile table) plus the HBM-resident accumulation buffer."""
 
     def __init__(self, profile=PROFILE_V2, math_mode=MATH_PARITY, num_bounces=-1, device=0, env_kind=None,
-                 env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False):
+                 env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False,
+                 disable_camera_culling=False):
         self._lib = load_library()
         self._ctx = ctypes.c_void_p()
         p = default_params(profile)
         p.math_mode, p.num_bounces, p.device = math_mode, num_bounces, device
         p.accum_mode, p.output_to_screen = accum_mode, int(bool(output_to_screen))
+        p.disable_camera_culling = int(bool(disable_camera_culling))
         if env_kind is not None:
             p.env_kind = env_kind
         if env_sampler is not None:
@@ -247,6 +250,18 @@ class Renderer:
 
     def finalize_sum(self, total_frames):
         self._check(self._lib.b200pt_finalize_sum(self._ctx, int(total_frames)), "b200pt_finalize_sum")
+
+
+def cull_rects(profile, width, height):
+    """Host-only: the conservative fragCoord-space rectangles used for camera-ray culling, or None."""
+    r = (ctypes.c_float * 48)()
+    n = ctypes.c_int32()
+    rc = load_library().b200pt_compute_cull_rects(profile, width, height, r, ctypes.byref(n))
+    if rc != 0:
+        raise B200PTError("b200pt_compute_cull_rects: invalid argument")
+    if n.value < 0:
+        return None
+    return np.array(r[:4 * n.value], dtype=np.float32).reshape(n.value, 4)
 
 
 def detile(buf, width, height, ntx, nty):

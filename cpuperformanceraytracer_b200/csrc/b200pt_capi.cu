@@ -370,6 +370,7 @@ int b200pt_render_frames(b200pt_context* c, int32_t nframes)
     rp.nframes = nframes;
     rp.num_bounces = c->params.num_bounces;
     rp.cameraDistance = c->cameraDistance;
+    rp.num_cull_rects = c->params.disable_camera_culling ? -1 : compute_cull_rects(c->params.profile, c->width, c->height, rp.cull_rect);
 
     LaunchConfig lc = launch_config(c);
     // persistent grid: every SM holds blocks_per_sm resident CTAs; warps pull 32-pixel items
@@ -536,6 +537,19 @@ int b200pt_download_rng_state(b200pt_context* c, uint32_t* host_dst)
     CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_rng, (size_t)c->width * c->height * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                 c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    return B200PT_OK;
+}
+
+int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float* rects, int32_t* count)
+{
+    if (!rects || !count || width <= 0 || height <= 0 || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_OPT_V4)
+        return B200PT_ERR_INVALID_ARGUMENT;
+    float4 r[kMaxCullRects];
+    const int n = compute_cull_rects(profile, width, height, r);
+    *count = n;
+    for (int i = 0; i < n; i++) {
+        rects[4 * i + 0] = r[i].x; rects[4 * i + 1] = r[i].y; rects[4 * i + 2] = r[i].z; rects[4 * i + 3] = r[i].w;
+    }
     return B200PT_OK;
 }
 

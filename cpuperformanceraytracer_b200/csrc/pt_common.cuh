@@ -52,6 +52,8 @@ struct V4Scene {
     float cameraDistance;
 };
 
+constexpr int kMaxCullRects = 12;
+
 struct DeviceCounters {
     unsigned long long segments;
     unsigned long long escapes;
@@ -75,6 +77,11 @@ struct RenderParams {
     int nframes;
     int num_bounces;
     float cameraDistance;     // 1 / tan(FOV/2), computed on the host like v2.cpp:546
+    // conservative screen-space bounds of the scene's primitives in fragCoord space
+    // (x0, y0, x1, y1; y = flipped row): a pixel whose jitter footprint overlaps none of them cannot
+    // hit anything, so its paths skip the scene trace (host/scene_setup.cpp: compute_cull_rects)
+    int num_cull_rects;       // < 0: culling disabled
+    float4 cull_rect[kMaxCullRects];
 };
 
 enum : int { kProfileV2 = 0, kProfileSimtTextured = 1, kProfileV4 = 2 };

@@ -133,4 +133,98 @@ void build_v4_scene(V4Scene* s)
     s->cameraPosition = mk(0.f, 0.f, 1.f * 40.f);  // v4.cpp:1501
 }
 
+
+// ---- camera-ray culling ---------------------------------------------------------------------------
+// A camera ray through fragCoord (fx, fy) has direction (tx, ty / aspect, camDist) with
+// tx = fx / W * 2 - 1, ty = fy / H * 2 - 1 from the origin (v2.cpp:543-560), or
+// (tx, ty * H / W, -camDist) from (0, 0, 40) (v4.cpp:1108-1121).  A primitive can only be hit by
+// rays whose fragCoord lies inside the projection of its bounding box.  The boxes are projected in
+// double precision and grown by 2 pixels + 0.1 %, three orders of magnitude more than the binary32
+// error of the reference's edge tests, so "outside every rectangle" implies that every sign test
+// of the reference fails by a wide margin (tests/test_cull_rects.py checks it against the oracle).
+namespace {
+struct Box { double lo[3], hi[3]; };
+
+bool project_box(const Box& b, int profile, int W, int H, double camDist, float4* out)
+{
+    double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
+    for (int k = 0; k < 8; k++) {
+        const double px = (k & 1) ? b.hi[0] : b.lo[0], py = (k & 2) ? b.hi[1] : b.lo[1], pz = (k & 4) ? b.hi[2] : b.lo[2];
+        double tx, ty;
+        if (profile == kProfileV4) {
+            const double depth = (40.0 - pz) / camDist;  // camera at (0, 0, 40) looking down -z
+            if (depth < 1e-3) return false;
+            tx = px / depth;
+            ty = py / depth * ((double)W / (double)H);
+        } else {
+            const double depth = pz / camDist;  // camera at the origin looking down +z
+            if (depth < 1e-3) return false;
+            tx = px / depth;
+            ty = py / depth * ((double)W / (double)H);  // ty / aspect = y / depth
+        }
+        const double fx = (tx + 1.0) * 0.5 * W, fy = (ty + 1.0) * 0.5 * H;
+        x0 = fx < x0 ? fx : x0; x1 = fx > x1 ? fx : x1;
+        y0 = fy < y0 ? fy : y0; y1 = fy > y1 ? fy : y1;
+    }
+    const double mx = 2.0 + 1e-3 * (x1 - x0 + W), my = 2.0 + 1e-3 * (y1 - y0 + H);
+    *out = make_float4((float)(x0 - mx), (float)(y0 - my), (float)(x1 + mx), (float)(y1 + my));
+    return true;
+}
+
+void grow(Box* b, const v3& p)
+{
+    const double c[3] = {p.x, p.y, p.z};
+    for (int a = 0; a < 3; a++) {
+        if (c[a] < b->lo[a]) b->lo[a] = c[a];
+        if (c[a] > b->hi[a]) b->hi[a] = c[a];
+    }
+}
+Box empty_box()
+{
+    Box b;
+    for (int a = 0; a < 3; a++) { b.lo[a] = 1e300; b.hi[a] = -1e300; }
+    return b;
+}
+Box sphere_box(const float4& s)
+{
+    Box b;
+    const double c[3] = {s.x, s.y, s.z};
+    for (int a = 0; a < 3; a++) { b.lo[a] = c[a] - 1.001 * s.w; b.hi[a] = c[a] + 1.001 * s.w; }
+    return b;
+}
+}  // namespace
+
+int compute_cull_rects(int profile, int width, int height, float4* rects)
+{
+    const double camDist = camera_distance();
+    int n = 0;
+    if (profile == kProfileV4) {
+        V4Scene s;
+        build_v4_scene(&s);
+        // the quad table only keeps V0 and edge bivectors; rebuild the vertex boxes from the source data
+        const double T = 10.0;
+        const double q[kV4Quads][2][3] = {{{-25, -12.5, -5 + T}, {25, -12.5, 5 + T}},
+                                          {{-25, -10.5, 5}, {25, -1.5, 5}},
+                                          {{-7.5, 12.5, -5 + T}, {7.5, 12.5, 5 + T}},
+                                          {{-5, 12.4, -2.5 + T}, {5, 12.4, 2.5 + T}}};
+        for (int i = 0; i < kV4Quads; i++) {
+            Box b;
+            for (int a = 0; a < 3; a++) { b.lo[a] = q[i][0][a] - 1e-3; b.hi[a] = q[i][1][a] + 1e-3; }
+            if (!project_box(b, profile, width, height, camDist, &rects[n++])) return -1;
+        }
+        for (int i = 0; i < kV4Spheres; i++)
+            if (!project_box(sphere_box(s.sphere[i]), profile, width, height, camDist, &rects[n++])) return -1;
+    } else {
+        CornellScene s;
+        build_cornell_scene(&s, profile == kProfileSimtTextured);
+        // the whole box in one rectangle (walls enclose light and spheres), plus nothing else
+        Box b = empty_box();
+        for (int i = 0; i < kCornellQuads; i++) { grow(&b, s.quad[i].a); grow(&b, s.quad[i].b); grow(&b, s.quad[i].c); grow(&b, s.quad[i].d); }
+        for (int i = 0; i < kCornellSpheres; i++) { const Box sb = sphere_box(s.sphere[i]); grow(&b, mk((float)sb.lo[0], (float)sb.lo[1], (float)sb.lo[2])); grow(&b, mk((float)sb.hi[0], (float)sb.hi[1], (float)sb.hi[2])); }
+        for (int a = 0; a < 3; a++) { b.lo[a] -= 1e-3; b.hi[a] += 1e-3; }
+        if (!project_box(b, profile, width, height, camDist, &rects[n++])) return -1;
+    }
+    return n;
+}
+
 }  // namespace b200pt

@@ -89,7 +89,9 @@ typedef struct b200pt_params {
     int32_t accum_mode;   /* B200PT_ACCUM_* */
     int32_t output_to_screen; /* OUTPUT_TO_SCREEN (global_preprocessor_flags.h:58): tone-map into the
                                  screen buffer after every render call */
-    int32_t reserved[7];
+    int32_t disable_camera_culling; /* 1: trace the scene even for pixels whose jitter footprint provably
+                                       misses every primitive (A/B measurements; results are identical) */
+    int32_t reserved[6];
 } b200pt_params;
 
 typedef struct b200pt_counters {
@@ -167,6 +169,11 @@ int b200pt_finalize_sum(b200pt_context* ctx, int32_t total_frames);
 /* debug/parity hook: u32 RNG state of every pixel after the last rendered frame's path ended
  * (row-major W*H, row 0 = top); checks wang_hash stream parity bit for bit */
 int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
+
+/* Host-only helper (no GPU needed): the conservative fragCoord-space rectangles (x0, y0, x1, y1;
+ * y = flipped row index) outside of which a camera ray of `profile` cannot hit the scene; the kernel
+ * skips the scene trace for such pixels.  rects must hold 4 * 12 floats; *count < 0 = no culling. */
+int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float* rects, int32_t* count);
 
 int b200pt_get_counters(b200pt_context* ctx, b200pt_counters* out);
 const char* b200pt_last_error(b200pt_context* ctx);

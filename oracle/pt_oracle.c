@@ -893,3 +893,22 @@ void oracle_pm_asinf_array(const float* x, float* out, int64_t n)
 {
     for (int64_t i = 0; i < n; i++) out[i] = pm_asinf(x[i]);
 }
+
+/* max number of traced segments over frames [first_frame, first_frame+nframes) for every pixel
+ * (row-major, row 0 = top): 1 means every path of the pixel escaped on its camera ray */
+int oracle_max_segments(const oracle_params* p, int first_frame, int nframes, uint32_t* out)
+{
+    ctx_t c;
+    if (ctx_init(&c, p) || !out) return -1;
+    for (int y = 0; y < p->height; y++)
+        for (int x = 0; x < p->width; x++) {
+            uint32_t mx = 0;
+            for (int f = 0; f < nframes; f++) {
+                path_stats_t st = {0, 0};
+                mainImage(&c, x, p->height - 1 - y, first_frame + f, 0, &st);
+                if (st.segments > mx) mx = (uint32_t)st.segments;
+            }
+            out[(size_t)y * p->width + x] = mx;
+        }
+    return 0;
+}

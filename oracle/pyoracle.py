@@ -106,6 +106,18 @@ def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, en
     return target, {"paths": cnt.paths, "segments": cnt.segments, "escapes": cnt.escapes}
 
 
+def max_segments(profile, width, height, bounces, nframes, first_frame=1, env=None, env_kind=ENV_NONE,
+                 env_sampler=SAMPLER_POINT):
+    """(H, W) uint32: max traced segments per pixel over the frame range."""
+    p, keep = make_params(profile, width, height, 1, 1, bounces, env, env_kind, env_sampler)
+    out = np.zeros(width * height, dtype=np.uint32)
+    L = lib()
+    L.oracle_max_segments.argtypes = [ctypes.POINTER(OracleParams), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)]
+    if L.oracle_max_segments(ctypes.byref(p), first_frame, nframes, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32))) != 0:
+        raise ValueError("oracle_max_segments: invalid parameters")
+    return out.reshape(height, width)
+
+
 def resolve_ldr(target, width, height, ntx, nty, mode=0):
     t = np.ascontiguousarray(target, dtype=np.float32)
     out = np.zeros(width * height, dtype=np.uint32)

@@ -198,3 +198,25 @@ def test_full_size_properties():
         r.render_frames(5)
         b = r.download_target()
     assert np.array_equal(a, b) and np.isfinite(a).all() and a.min() >= 0
+
+
+@pytest.mark.parametrize("profile,envshape,ek,es", [(api.PROFILE_V2, None, None, None), (api.PROFILE_OPT_V4, (128, 64), 1, 2),
+                                                    (api.PROFILE_SIMT_TEXTURED, (128, 64), None, None)],
+                         ids=["v2", "v4", "simt_textured"])
+def test_camera_culling_changes_nothing(oracle, profile, envshape, ek, es):
+    """Skipping the scene trace for pixels whose jitter footprint misses every primitive's screen
+    bounds must not change a single bit (buffer, RNG states, counters)."""
+    W, H, ntx, nty, frames = 384, 216, 4, 6, 10
+    env = oracle.synthetic_env(*envshape) if envshape else None
+    res = []
+    for off in (False, True):
+        kw = dict(env_kind=ek, env_sampler=es) if profile == api.PROFILE_OPT_V4 else {}
+        with api.Renderer(profile=profile, num_bounces=8, disable_camera_culling=off, **kw) as r:
+            if env is not None:
+                r.set_env(env)
+            r.resize(W, H, ntx, nty)
+            r.render_frames(frames)
+            c = r.counters()
+            res.append((r.download_target(), r.rng_state(), c["segments"], c["escapes"]))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+    assert res[0][2:] == res[1][2:]
