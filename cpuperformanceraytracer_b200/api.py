@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters", "b200pt_compute_cull_rects",
+    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range",
 ]
 
 
@@ -89,6 +89,7 @@ def load_library():
     L.b200pt_get_device_target.argtypes = [vp, ctypes.POINTER(vp), ctypes.POINTER(ctypes.c_size_t)]
     L.b200pt_set_stream.argtypes = [vp, vp]
     L.b200pt_finalize_sum.argtypes = [vp, i32]
+    L.b200pt_set_tile_row_range.argtypes = [vp, i32, i32]
     L.b200pt_download_rng_state.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.b200pt_get_counters.argtypes = [vp, ctypes.POINTER(Counters)]
     L.b200pt_compute_cull_rects.argtypes = [ctypes.c_int, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
@@ -247,6 +248,10 @@ class Renderer:
 
     def set_stream(self, cuda_stream_ptr):
         self._check(self._lib.b200pt_set_stream(self._ctx, ctypes.c_void_p(cuda_stream_ptr)), "b200pt_set_stream")
+
+    def set_tile_row_range(self, first_tile_row, num_tile_rows):
+        self._check(self._lib.b200pt_set_tile_row_range(self._ctx, int(first_tile_row), int(num_tile_rows)),
+                    "b200pt_set_tile_row_range")
 
     def finalize_sum(self, total_frames):
         self._check(self._lib.b200pt_finalize_sum(self._ctx, int(total_frames)), "b200pt_finalize_sum")

@@ -46,6 +46,7 @@ struct b200pt_context {
     const float* last_env_ptr = nullptr;
 
     int iframe = 0;
+    int first_tile_row = 0, num_tile_rows = 0;  // band rendered by this context (0, 0 = all rows)
     int blocks_per_sm = 0;
     uint64_t paths = 0, launches = 0;
     double last_render_ms = 0.0;
@@ -311,6 +312,7 @@ int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx,
     c->nty = nty;
     c->tile_w = width / ntx;
     c->tile_h = height / nty;
+    c->first_tile_row = c->num_tile_rows = 0;
     return b200pt_reset(c);
 }
 
@@ -364,7 +366,10 @@ int b200pt_render_frames(b200pt_context* c, int32_t nframes)
     rp.num_tiles_x = c->ntx;
     rp.groups_per_tile_row = c->tile_w / 8;
     rp.groups_per_tile = rp.groups_per_tile_row * c->tile_h;
-    rp.num_groups = c->width * c->height / 8;
+    const int groups_per_tile_band = rp.groups_per_tile * c->ntx;  // one row of tiles is contiguous in memory
+    const int band_rows = c->num_tile_rows > 0 ? c->num_tile_rows : c->nty;
+    rp.group_offset = (c->num_tile_rows > 0 ? c->first_tile_row : 0) * groups_per_tile_band;
+    rp.num_groups = band_rows * groups_per_tile_band;
     rp.num_items = (rp.num_groups + 3) / 4;
     rp.first_frame = c->iframe + 1;  // iFrame += 1 before the render, v4.cpp:1703
     rp.nframes = nframes;
@@ -390,7 +395,7 @@ int b200pt_render_frames(b200pt_context* c, int32_t nframes)
     c->timing_pending = true;
     c->launches++;
     c->iframe += nframes;
-    c->paths += (uint64_t)c->width * c->height * (uint64_t)nframes;
+    c->paths += (uint64_t)rp.num_groups * 8u * (uint64_t)nframes;
 
     if (c->params.output_to_screen) {  // OUTPUT_TO_SCREEN: per-render tone map, v4.cpp:1562-1564
         CUDA_TRY(c, launch_resolve_ldr(c->d_target, c->d_screen, c->width, c->height, c->tile_w, c->tile_h, c->ntx,
@@ -515,6 +520,17 @@ int b200pt_set_stream(b200pt_context* c, void* cuda_stream)
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
+    return B200PT_OK;
+}
+
+int b200pt_set_tile_row_range(b200pt_context* c, int32_t first_tile_row, int32_t num_tile_rows)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    if (first_tile_row < 0 || num_tile_rows < 0 || first_tile_row + num_tile_rows > c->nty)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "tile row range outside the image");
+    c->first_tile_row = first_tile_row;
+    c->num_tile_rows = num_tile_rows;
     return B200PT_OK;
 }
 

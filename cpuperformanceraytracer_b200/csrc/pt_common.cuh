@@ -71,7 +71,8 @@ struct RenderParams {
     int tile_w, tile_h, num_tiles_x;
     int groups_per_tile_row;  // tile_w / 8
     int groups_per_tile;      // tile_w / 8 * tile_h
-    int num_groups;           // width * height / 8
+    int num_groups;           // SoA8 groups rendered by this launch (whole image, or a band of tile rows)
+    int group_offset;         // first group of the band (tile-shard: a rank's tile rows are contiguous)
     int num_items;            // ceil(num_groups / 4): one warp = 4 groups = 32 pixels
     int first_frame;          // 1-based iFrame of the first render call in this launch
     int nframes;

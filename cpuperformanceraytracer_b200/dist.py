@@ -100,3 +100,43 @@ class SppShardedRenderer:
 
     def close(self):
         self.r.close()
+
+
+class TileShardedRenderer:
+    """tile-shard render: rank r renders tile rows [a, b) of every frame with the reference's running
+    average (bit-identical to a single-GPU render); the contiguous spans are then exchanged so that
+    every rank holds the whole image (one broadcast per rank span; spans may differ in size)."""
+
+    def __init__(self, renderer_factory, width, height, ntx, nty, rank, world_size, device):
+        import torch
+        from . import api
+        self.torch = torch
+        self.rank, self.world = rank, world_size
+        self.device = torch.device("cuda", device)
+        self.shards = [shard_tile_rows(width, height, nty, world_size, r) for r in range(world_size)]
+        self.r = renderer_factory(accum_mode=api.ACCUM_RUNNING_AVERAGE, device=device)
+        self.r.resize(width, height, ntx, nty)
+        self.buf = torch.zeros(width * height * 3, dtype=torch.float32, device=self.device)
+        self.r.bind_device_target(self.buf.data_ptr())
+        me = self.shards[rank]
+        self.r.set_tile_row_range(me.first_tile_row, me.num_tile_rows)
+        self.stream = torch.cuda.Stream(self.device)
+        self.r.set_stream(self.stream.cuda_stream)
+        torch.cuda.synchronize(self.device)
+
+    def render(self, nframes, gather=True):
+        """nframes more render calls on this rank's rows (frame counter carries on), then the exchange."""
+        import torch.distributed as dist
+        with self.torch.cuda.stream(self.stream):
+            if self.shards[self.rank].num_tile_rows > 0:
+                self.r.render_frames(nframes, sync=False)
+            else:
+                self.r.frame_counter = self.r.frame_counter + nframes
+            if gather and self.world > 1:
+                for src, sh in enumerate(self.shards):
+                    if sh.float_count:
+                        dist.broadcast(self.buf[sh.float_offset:sh.float_offset + sh.float_count], src=src)
+        return self.buf
+
+    def close(self):
+        self.r.close()

@@ -162,6 +162,10 @@ int b200pt_bind_device_target(b200pt_context* ctx, void* device_ptr);
 int b200pt_get_device_target(b200pt_context* ctx, void** device_ptr, size_t* bytes);
 /* launch on a caller-owned cudaStream_t (NULL = the context's own stream) */
 int b200pt_set_stream(b200pt_context* ctx, void* cuda_stream);
+/* tile-shard: restrict render calls to tile rows [first, first + count) -- one contiguous span of the
+ * band-major buffer (float offset first * TileHeight * W * 3).  (0, 0) = all rows (default after resize).
+ * The render is bit-identical to the same rows of a full render. */
+int b200pt_set_tile_row_range(b200pt_context* ctx, int32_t first_tile_row, int32_t num_tile_rows);
 /* ACCUM_SUM epilogue: target *= 1/(total_frames + 1), the value the reference's running average
  * converges to after total_frames render calls on a zeroed buffer */
 int b200pt_finalize_sum(b200pt_context* ctx, int32_t total_frames);

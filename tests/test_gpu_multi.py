@@ -34,10 +34,14 @@ sr = ptdist.SppShardedRenderer(factory, W, H, ntx, nty, rank, world, local)
 buf = sr.render(total)
 sr.stream.synchronize()
 out = buf.cpu().numpy()
+tr = ptdist.TileShardedRenderer(factory, W, H, ntx, nty, rank, world, local)
+tbuf = tr.render(total)
+tr.stream.synchronize()
+tout = tbuf.cpu().numpy()
 if rank == 0:
     with factory() as r:
         r.resize(W, H, ntx, nty); r.render_frames(total); seq = r.download_target()
-    np.save(sys.argv[1], np.stack([out, seq]))
+    np.save(sys.argv[1], np.stack([out, seq, tout]))
 tdist.barrier(); tdist.destroy_process_group()
 '''
 
@@ -50,6 +54,8 @@ def test_spp_shard_matches_sequential(tmp_path):
     n = min(_ngpus(), 4)
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
                     "127.0.0.1", "--master-port", "29541", str(script), str(out)], check=True, timeout=600)
-    sharded, seq = np.load(out)
+    sharded, seq, tiled = np.load(out)
     # same samples, different summation order (sum then scale vs running average): ~1e-6 relative
     assert np.allclose(sharded, seq, rtol=3e-6, atol=3e-6)
+    # tile-shard: bit-identical to the single-GPU render
+    assert np.array_equal(tiled, seq)

@@ -220,3 +220,18 @@ def test_camera_culling_changes_nothing(oracle, profile, envshape, ek, es):
             res.append((r.download_target(), r.rng_state(), c["segments"], c["escapes"]))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
     assert res[0][2:] == res[1][2:]
+
+
+def test_tile_row_bands_assemble_to_the_full_render(oracle):
+    """tile-shard building block: rendering tile rows band by band == the full render, bit for bit."""
+    W, H, ntx, nty, frames = 192, 120, 3, 5, 9
+    o, _ = oracle.render(oracle.PROFILE_V2, W, H, ntx, nty, 8, frames)
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=8) as r:
+        r.resize(W, H, ntx, nty)
+        for first, count in ((3, 2), (0, 1), (1, 2)):
+            r.frame_counter = 0
+            r.set_tile_row_range(first, count)
+            r.render_frames(frames)
+        assert np.array_equal(r.download_target(), o)
+        with pytest.raises(api.B200PTError):
+            r.set_tile_row_range(4, 2)
