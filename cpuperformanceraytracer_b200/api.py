@@ -41,7 +41,8 @@ class Params(ctypes.Structure):
     _fields_ = [("struct_size", ctypes.c_int32), ("device", ctypes.c_int32), ("profile", ctypes.c_int32),
                 ("math_mode", ctypes.c_int32), ("num_bounces", ctypes.c_int32), ("env_kind", ctypes.c_int32),
                 ("env_sampler", ctypes.c_int32), ("accum_mode", ctypes.c_int32), ("output_to_screen", ctypes.c_int32),
-                ("disable_camera_culling", ctypes.c_int32), ("reserved", ctypes.c_int32 * 6)]
+                ("disable_camera_culling", ctypes.c_int32), ("generic_scene_tables", ctypes.c_int32),
+                ("reserved", ctypes.c_int32 * 5)]
 
 
 class Counters(ctypes.Structure):
@@ -115,13 +116,14 @@ class Renderer:
 
     def __init__(self, profile=PROFILE_V2, math_mode=MATH_PARITY, num_bounces=-1, device=0, env_kind=None,
                  env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False,
-                 disable_camera_culling=False):
+                 disable_camera_culling=False, generic_scene_tables=False):
         self._lib = load_library()
         self._ctx = ctypes.c_void_p()
         p = default_params(profile)
         p.math_mode, p.num_bounces, p.device = math_mode, num_bounces, device
         p.accum_mode, p.output_to_screen = accum_mode, int(bool(output_to_screen))
         p.disable_camera_culling = int(bool(disable_camera_culling))
+        p.generic_scene_tables = int(bool(generic_scene_tables))
         if env_kind is not None:
             p.env_kind = env_kind
         if env_sampler is not None:

@@ -88,6 +88,7 @@ LaunchConfig launch_config(const b200pt_context* c)
                          ? c->params.env_sampler
                          : kSamplerPoint;
     lc.accum_mode = c->params.accum_mode;
+    lc.static_scene = c->params.generic_scene_tables ? 0 : 1;
     lc.block = 256;
     lc.grid = 1;
     return lc;

@@ -27,6 +27,18 @@ struct LegacyMaterial {
 constexpr int kCornellQuads = 6;
 constexpr int kCornellSpheres = 3;
 constexpr int kCornellObjects = kCornellQuads + kCornellSpheres;
+// The Cornell box is hard-coded in the reference (literals of v2.cpp:328-331,345-348,362-365,379-382,
+// 396-399,413-416 plus sceneTranslation :323).  One table feeds both the host-built CornellScene and
+// the kernel's compile-time specialisation, in which the vertex coordinates are immediates so that
+// the 72 "vertex - rayPos" subtractions of a trace collapse to the 15 distinct ones.
+constexpr float kCornellTranslation[3] = {0.0f, 0.0f, 10.0f};
+constexpr float kCornellQuadVerts[kCornellQuads][4][3] = {
+    {{-12.6f, -12.6f, 25.0f}, {12.6f, -12.6f, 25.0f}, {12.6f, 12.6f, 25.0f}, {-12.6f, 12.6f, 25.0f}},        // back wall
+    {{-12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 15.0f}, {-12.6f, -12.45f, 15.0f}},  // floor
+    {{-12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 15.0f}, {-12.6f, 12.5f, 15.0f}},          // ceiling
+    {{-12.5f, -12.6f, 25.0f}, {-12.5f, -12.6f, 15.0f}, {-12.5f, 12.6f, 15.0f}, {-12.5f, 12.6f, 25.0f}},      // left wall
+    {{12.5f, -12.6f, 25.0f}, {12.5f, -12.6f, 15.0f}, {12.5f, 12.6f, 15.0f}, {12.5f, 12.6f, 25.0f}},          // right wall
+    {{-5.0f, 12.4f, 22.5f}, {5.0f, 12.4f, 22.5f}, {5.0f, 12.4f, 17.5f}, {-5.0f, 12.4f, 17.5f}}};             // light
 struct CornellScene {
     LegacyQuad quad[kCornellQuads];
     float4 sphere[kCornellSpheres];  // xyz + radius
@@ -92,6 +104,7 @@ enum : int { kAccumAverage = 0, kAccumSum = 1 };
 
 struct LaunchConfig {
     int profile, env_kind, env_sampler, accum_mode;
+    int static_scene;  // Cornell profiles: vertex coordinates as immediates (same bits, fewer instructions)
     int grid, block;
 };
 

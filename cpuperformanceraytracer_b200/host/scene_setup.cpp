@@ -40,14 +40,8 @@ float camera_distance()
 void build_cornell_scene(CornellScene* s, bool simt_textured_materials)
 {
     std::memset(s, 0, sizeof(*s));
-    const v3 T = mk(0.0f, 0.0f, 10.0f);  // sceneTranslation, v2.cpp:323
-    static const float Q[kCornellQuads][4][3] = {
-        {{-12.6f, -12.6f, 25.0f}, {12.6f, -12.6f, 25.0f}, {12.6f, 12.6f, 25.0f}, {-12.6f, 12.6f, 25.0f}},        // back wall  :328-331
-        {{-12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 15.0f}, {-12.6f, -12.45f, 15.0f}},  // floor      :345-348
-        {{-12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 15.0f}, {-12.6f, 12.5f, 15.0f}},          // ceiling    :362-365
-        {{-12.5f, -12.6f, 25.0f}, {-12.5f, -12.6f, 15.0f}, {-12.5f, 12.6f, 15.0f}, {-12.5f, 12.6f, 25.0f}},      // left wall  :379-382
-        {{12.5f, -12.6f, 25.0f}, {12.5f, -12.6f, 15.0f}, {12.5f, 12.6f, 15.0f}, {12.5f, 12.6f, 25.0f}},          // right wall :396-399
-        {{-5.0f, 12.4f, 22.5f}, {5.0f, 12.4f, 22.5f}, {5.0f, 12.4f, 17.5f}, {-5.0f, 12.4f, 17.5f}}};             // light      :413-416
+    const v3 T = mk(kCornellTranslation[0], kCornellTranslation[1], kCornellTranslation[2]);  // sceneTranslation, v2.cpp:323
+    const auto& Q = kCornellQuadVerts;  // v2.cpp:328-331,345-348,362-365,379-382,396-399,413-416
     for (int i = 0; i < kCornellQuads; i++) {
         LegacyQuad& q = s->quad[i];
         q.a = add(mk(Q[i][0][0], Q[i][0][1], Q[i][0][2]), T);

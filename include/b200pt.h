@@ -91,7 +91,9 @@ typedef struct b200pt_params {
                                  screen buffer after every render call */
     int32_t disable_camera_culling; /* 1: trace the scene even for pixels whose jitter footprint provably
                                        misses every primitive (A/B measurements; results are identical) */
-    int32_t reserved[6];
+    int32_t generic_scene_tables;   /* 1: read the Cornell vertices from the scene table instead of the
+                                       compile-time specialisation (A/B measurements; results are identical) */
+    int32_t reserved[5];
 } b200pt_params;
 
 typedef struct b200pt_counters {

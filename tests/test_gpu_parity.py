@@ -235,3 +235,19 @@ def test_tile_row_bands_assemble_to_the_full_render(oracle):
         assert np.array_equal(r.download_target(), o)
         with pytest.raises(api.B200PTError):
             r.set_tile_row_range(4, 2)
+
+
+@pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED], ids=["v2", "simt_textured"])
+def test_static_scene_specialisation_changes_nothing(oracle, profile):
+    """Cornell vertices as immediates (default) vs read from the scene table: identical bits."""
+    W, H, ntx, nty, frames = 256, 160, 4, 5, 10
+    env = oracle.synthetic_env(128, 64) if profile == api.PROFILE_SIMT_TEXTURED else None
+    res = []
+    for generic in (False, True):
+        with api.Renderer(profile=profile, num_bounces=8, generic_scene_tables=generic) as r:
+            if env is not None:
+                r.set_env(env)
+            r.resize(W, H, ntx, nty)
+            r.render_frames(frames)
+            res.append((r.download_target(), r.rng_state()))
+    assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
