@@ -28,6 +28,9 @@ ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "-fPIC", "-Xcompiler",
           "-ffp-contract=off", "-I", os.path.join(ROOT, "include")]
 IEEE = ["--fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
+# tuning knob for experiments: minimum resident CTAs per SM handed to __launch_bounds__
+if os.environ.get("B200PT_MIN_BLOCKS"):
+    COMMON = COMMON + ["-DB200PT_MIN_BLOCKS=" + os.environ["B200PT_MIN_BLOCKS"]]
 
 UNITS = [
     # (source, object, extra flags)
