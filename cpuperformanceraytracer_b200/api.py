@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range",
+    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_present_submit", "b200pt_present_acquire",
 ]
 
 
@@ -91,6 +91,8 @@ def load_library():
     L.b200pt_set_stream.argtypes = [vp, vp]
     L.b200pt_finalize_sum.argtypes = [vp, i32]
     L.b200pt_set_tile_row_range.argtypes = [vp, i32, i32]
+    L.b200pt_present_submit.argtypes = [vp, i32]
+    L.b200pt_present_acquire.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(i32)]
     L.b200pt_download_rng_state.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.b200pt_get_counters.argtypes = [vp, ctypes.POINTER(Counters)]
     L.b200pt_compute_cull_rects.argtypes = [ctypes.c_int, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
@@ -226,6 +228,16 @@ class Renderer:
                                           int(bump_frame_counter))
         self._check(rc, "b200pt_resolve_ldr")
         return out
+
+    def present_submit(self, nframes=1):
+        self._check(self._lib.b200pt_present_submit(self._ctx, int(nframes)), "b200pt_present_submit")
+
+    def present_acquire(self, copy=True):
+        """Oldest in-flight frame as an (H, W) uint32 array (a view of pinned memory unless copy) + its iFrame."""
+        ptr, fr = ctypes.POINTER(ctypes.c_uint32)(), ctypes.c_int32()
+        self._check(self._lib.b200pt_present_acquire(self._ctx, ctypes.byref(ptr), ctypes.byref(fr)), "b200pt_present_acquire")
+        a = np.ctypeslib.as_array(ptr, shape=(self.height, self.width))
+        return (a.copy() if copy else a), fr.value
 
     def rng_state(self):
         out = np.empty((self.height, self.width), dtype=np.uint32)

@@ -30,7 +30,13 @@ struct b200pt_context {
     int width = 0, height = 0, ntx = 0, nty = 0, tile_w = 0, tile_h = 0;
     float* d_target_own = nullptr;
     float* d_target = nullptr;  // own or bound
-    uint32_t* d_screen = nullptr;
+    uint32_t* d_screen = nullptr;       // slot 0 of the present ring; also used by resolve_ldr / render_host
+    uint32_t* d_screen1 = nullptr;      // slot 1
+    uint32_t* h_ring[2] = {nullptr, nullptr};  // pinned host frames of the present ring
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t render_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
+    int ring_frame[2] = {0, 0};
+    unsigned long long submitted = 0, acquired = 0;
     uint32_t* d_rng = nullptr;
     int* d_work_counter = nullptr;
     DeviceCounters* d_counters = nullptr;
@@ -98,6 +104,13 @@ void free_target(b200pt_context* c)
 {
     if (c->d_target_own) cudaFree(c->d_target_own);
     if (c->d_screen) cudaFree(c->d_screen);
+    if (c->d_screen1) cudaFree(c->d_screen1);
+    for (int i = 0; i < 2; i++) {
+        if (c->h_ring[i]) cudaFreeHost(c->h_ring[i]);
+        c->h_ring[i] = nullptr;
+    }
+    c->d_screen1 = nullptr;
+    c->submitted = c->acquired = 0;
     if (c->d_rng) cudaFree(c->d_rng);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
     if (c->h_pinned_screen) cudaFreeHost(c->h_pinned_screen);
@@ -208,6 +221,11 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     }
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->render_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->render_done[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_done[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_done[1], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
         cudaMalloc(&c->d_work_counter, sizeof(int)) != cudaSuccess ||
         cudaMalloc(&c->d_counters, sizeof(DeviceCounters)) != cudaSuccess ||
@@ -243,6 +261,11 @@ int b200pt_destroy(b200pt_context* c)
     free_env(c);
     if (c->d_work_counter) cudaFree(c->d_work_counter);
     if (c->d_counters) cudaFree(c->d_counters);
+    if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
+    for (int i = 0; i < 2; i++) {
+        if (c->render_done[i]) cudaEventDestroy(c->render_done[i]);
+        if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
+    }
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
@@ -343,7 +366,16 @@ int b200pt_get_frame_counter(b200pt_context* c, int32_t* iframe)
     return B200PT_OK;
 }
 
+static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* screen);
+
 int b200pt_render_frames(b200pt_context* c, int32_t nframes)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    // OUTPUT_TO_SCREEN: tone-map into the screen buffer as part of the render (v4.cpp:1562-1564)
+    return render_frames_impl(c, nframes, c->params.output_to_screen ? c->d_screen : nullptr);
+}
+
+static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* screen)
 {
     if (!c || nframes < 0) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
@@ -355,6 +387,8 @@ int b200pt_render_frames(b200pt_context* c, int32_t nframes)
     RenderParams rp{};
     rp.target = c->d_target;
     rp.rng_out = c->d_rng;
+    rp.screen = screen;
+    rp.screen_mode = B200PT_LDR_SCREEN_BGRA;
     rp.work_counter = c->d_work_counter;
     rp.counters = c->d_counters;
     rp.env = c->env_tex;
@@ -398,11 +432,6 @@ int b200pt_render_frames(b200pt_context* c, int32_t nframes)
     c->iframe += nframes;
     c->paths += (uint64_t)rp.num_groups * 8u * (uint64_t)nframes;
 
-    if (c->params.output_to_screen) {  // OUTPUT_TO_SCREEN: per-render tone map, v4.cpp:1562-1564
-        CUDA_TRY(c, launch_resolve_ldr(c->d_target, c->d_screen, c->width, c->height, c->tile_w, c->tile_h, c->ntx,
-                                       B200PT_LDR_SCREEN_BGRA, c->stream));
-        c->launches++;
-    }
     return B200PT_OK;
 }
 
@@ -488,12 +517,53 @@ int b200pt_resolve_ldr(b200pt_context* c, uint32_t* host_dst, int32_t mode, int3
     if (!c || !host_dst || (mode != B200PT_LDR_FILE_RGBA && mode != B200PT_LDR_SCREEN_BGRA)) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
     CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));  // the present ring may still be reading slot 0
     CUDA_TRY(c, launch_resolve_ldr(c->d_target, c->d_screen, c->width, c->height, c->tile_w, c->tile_h, c->ntx, mode, c->stream));
     c->launches++;
     CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_screen, (size_t)c->width * c->height * sizeof(uint32_t),
                                 cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (bump_frame_counter) c->iframe += 1;  // CopyOutputToFile: iFrame += 1.0f, v4.cpp:1741
+    return B200PT_OK;
+}
+
+// ---- progressive present path: the windowed loop of ApplicationState::RunApp
+// (Application.cpp:306-375) renders NUM_SAMPLES_PER_FRAME, tone-maps per tile (OutputToScreen) and
+// presents.  Here: render + fused tone map into one of two device frames, asynchronous copy to one of
+// two pinned host frames on a second stream, so the copy of frame k overlaps the render of frame k+1.
+int b200pt_present_submit(b200pt_context* c, int32_t nframes)
+{
+    if (!c || nframes <= 0) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    if (c->submitted - c->acquired >= 2) return fail(c, B200PT_ERR_NOT_READY, "present ring full: acquire a frame first");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const size_t bytes = (size_t)c->width * c->height * sizeof(uint32_t);
+    if (!c->d_screen1) CUDA_TRY(c, cudaMalloc(&c->d_screen1, bytes));
+    for (int i = 0; i < 2; i++)
+        if (!c->h_ring[i]) CUDA_TRY(c, cudaMallocHost(&c->h_ring[i], bytes));
+    const int slot = (int)(c->submitted & 1ull);
+    uint32_t* dscreen = slot ? c->d_screen1 : c->d_screen;
+    const int rc = render_frames_impl(c, nframes, dscreen);
+    if (rc != B200PT_OK) return rc;
+    CUDA_TRY(c, cudaEventRecord(c->render_done[slot], c->stream));
+    CUDA_TRY(c, cudaStreamWaitEvent(c->copy_stream, c->render_done[slot], 0));
+    CUDA_TRY(c, cudaMemcpyAsync(c->h_ring[slot], dscreen, bytes, cudaMemcpyDeviceToHost, c->copy_stream));
+    CUDA_TRY(c, cudaEventRecord(c->copy_done[slot], c->copy_stream));
+    c->ring_frame[slot] = c->iframe;
+    c->submitted++;
+    return B200PT_OK;
+}
+
+int b200pt_present_acquire(b200pt_context* c, const uint32_t** frame, int32_t* iframe)
+{
+    if (!c || !frame) return B200PT_ERR_INVALID_ARGUMENT;
+    if (c->acquired >= c->submitted) return fail(c, B200PT_ERR_NOT_READY, "no frame in flight");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    const int slot = (int)(c->acquired & 1ull);
+    CUDA_TRY(c, cudaEventSynchronize(c->copy_done[slot]));
+    *frame = c->h_ring[slot];
+    if (iframe) *iframe = c->ring_frame[slot];
+    c->acquired++;
     return B200PT_OK;
 }
 

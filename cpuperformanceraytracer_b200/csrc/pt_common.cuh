@@ -75,6 +75,8 @@ struct DeviceCounters {
 struct RenderParams {
     float* target;        // tile-major SoA8 accumulation buffer (RenderTile, v4.cpp:1189-1252)
     uint32_t* rng_out;    // optional: final RNG state per pixel, row-major (debug/parity)
+    uint32_t* screen;     // optional: row-major u32 image, tone-mapped in the kernel tail (OUTPUT_TO_SCREEN)
+    int screen_mode;      // 0 = file packing, 1 = screen packing
     int* work_counter;    // atomic work-item counter: replaces work_queue.cpp's ring + CAS pop
     DeviceCounters* counters;
     cudaTextureObject_t env;  // RGBA32F linear texture, texel t = reference float index 3t

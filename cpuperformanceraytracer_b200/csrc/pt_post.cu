@@ -6,40 +6,9 @@
 //   pack_env    : RGB f32 rows -> RGBA32F texels for the env texture object.
 // Compiled with --fmad=false so the tone map rounds like the reference's explicit fmadd sequence.
 #include "pt_common.cuh"
+#include "pt_tonemap.cuh"
 
 namespace b200pt {
-
-__device__ __forceinline__ float max_ps_(float a, float b) { return a > b ? a : b; }
-__device__ __forceinline__ float min_ps_(float a, float b) { return a < b ? a : b; }
-__device__ __forceinline__ float saturate_(float x) { return min_ps_(max_ps_(x, 0.f), 1.f); }
-__device__ __forceinline__ float rcp_(float a) { return __fdiv_rn(1.0f, a); }
-
-__device__ __forceinline__ float fast_pow_gamma(float x)
-{
-    const float sqrtx = __fsqrt_rn(x);
-    const float onethird = 1.f / 3.f, twothirds = 2.f / 3.f;
-    const float nit1 = fmaf(sqrtx, twothirds, onethird);
-    const float nit2 = fmaf(nit1, twothirds, (x * rcp_(nit1 * nit1)) * onethird);
-    const float nit3 = fmaf(nit2, twothirds, (x * rcp_(nit2 * nit2)) * onethird);
-    return __fsqrt_rn(sqrtx * nit3);
-}
-__device__ __forceinline__ float aces1(float X)
-{
-    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
-    const float rcpDenom = rcp_(fmaf(X, fmaf(c, X, d), e));
-    return saturate_((X * fmaf(a, X, b)) * rcpDenom);
-}
-__device__ __forceinline__ float srgb1(float v)
-{
-    v = saturate_(v);
-    return (v < 0.0031308f) ? v * 12.92f : fmaf(1.055f, fast_pow_gamma(v), -0.055f);
-}
-__device__ __forceinline__ uint32_t quant(float c)
-{
-    float v = srgb1(aces1(c * 1.0f));
-    v = saturate_(v) * 255.f;
-    return (uint32_t)__float2int_rn(v) & 0xFFu;
-}
 
 // one thread per pixel; a warp reads 4 SoA8 groups (384 contiguous bytes) and writes 32
 // consecutive u32 of one image row
@@ -57,8 +26,7 @@ __global__ void resolve_ldr_kernel(const float* __restrict__ target, uint32_t* _
     const int ly = r / groups_per_tile_row, gx = r - ly * groups_per_tile_row;
     const int x = tx * tile_w + gx * 8 + l, y = ty * tile_h + ly;
     const float* px = target + g * 24 + l;
-    const uint32_t R = quant(px[0]), G = quant(px[8]), B = quant(px[16]);
-    out[(size_t)y * width + x] = (mode == 0) ? (0xFF000000u | (B << 16) | (G << 8) | R) : ((R << 16) | (G << 8) | B);
+    out[(size_t)y * width + x] = tonemap::pack(px[0], px[8], px[16], mode);
 }
 
 __global__ void scale_kernel(float* __restrict__ t, size_t n, float scale)

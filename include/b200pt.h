@@ -158,6 +158,14 @@ int b200pt_render_host(b200pt_context* ctx, float* BufferOut, int32_t BufferWidt
  * bump_frame_counter != 0 (..._optimization_v4.cpp:1741). */
 int b200pt_resolve_ldr(b200pt_context* ctx, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter);
 
+/* Progressive present path -- the windowed loop of ApplicationState::RunApp (Application.cpp:306-375):
+ * render nframes (NUM_SAMPLES_PER_FRAME), tone-map (OutputToScreen packing, fused into the render
+ * kernel) and copy the u32 frame to pinned host memory asynchronously.  Two frames can be in flight:
+ * submit k+1 overlaps the copy of k.  acquire blocks until the oldest submitted frame is in host
+ * memory; the returned pointer stays valid until two more submits. */
+int b200pt_present_submit(b200pt_context* ctx, int32_t nframes);
+int b200pt_present_acquire(b200pt_context* ctx, const uint32_t** frame, int32_t* iframe);
+
 /* multi-GPU plumbing: render into / reduce over a caller-owned device buffer (e.g. the storage of
  * a tensor handed to an NCCL all-reduce).  Pass NULL to go back to the internal buffer. */
 int b200pt_bind_device_target(b200pt_context* ctx, void* device_ptr);

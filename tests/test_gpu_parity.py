@@ -251,3 +251,30 @@ def test_static_scene_specialisation_changes_nothing(oracle, profile):
             r.render_frames(frames)
             res.append((r.download_target(), r.rng_state()))
     assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1])
+
+
+def test_present_ring_frames_are_the_reference_screen_frames(oracle):
+    """Progressive present path: frame k of the ring == OutputToScreen of the buffer after k render
+    calls (fused tone map in the render kernel, asynchronous double-buffered copy)."""
+    W, H, ntx, nty = 128, 72, 4, 6
+    cube = oracle.synthetic_env(32, 192)
+    with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=8, env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM,
+                      output_to_screen=True) as r:
+        r.set_env(cube)
+        r.resize(W, H, ntx, nty)
+        with pytest.raises(api.B200PTError):
+            r.present_acquire()  # nothing in flight
+        frames = []
+        r.present_submit(1)
+        for k in range(2, 7):
+            r.present_submit(1)                 # frame k renders while frame k-1 is copied
+            frames.append(r.present_acquire())
+        with pytest.raises(api.B200PTError):
+            r.present_submit(1); r.present_submit(1); r.present_submit(1)  # ring holds two frames
+        frames.append(r.present_acquire())
+    buf = np.zeros(W * H * 3, dtype=np.float32)
+    for k, (img, iframe) in enumerate(frames[:6], start=1):
+        buf, _ = oracle.render(oracle.PROFILE_V4, W, H, ntx, nty, 8, 1, first_frame=k, env=cube, env_kind=2, env_sampler=2,
+                               target=buf)
+        assert iframe == k
+        assert np.array_equal(img, oracle.resolve_ldr(buf, W, H, ntx, nty, mode=1)), k
