@@ -6,5 +6,5 @@ include/b200pt.h.  `api` is the ctypes handle; `build` compiles the library in-t
 """
 from . import api  # noqa: F401
 from .api import (ACCUM_RUNNING_AVERAGE, ACCUM_SUM, ENV_CUBEMAP, ENV_EQUIRECT, ENV_NONE, MATH_FAST, MATH_PARITY,  # noqa: F401
-                  PROFILE_OPT_V4, PROFILE_SIMT_TEXTURED, PROFILE_V2, SAMPLER_BILINEAR, SAMPLER_POINT, SAMPLER_RANDOM,
+                  PROFILE_OPT_V4, PROFILE_SIMT_TEXTURED, PROFILE_V2, PROFILE_V3_REDO, SAMPLER_BILINEAR, SAMPLER_POINT, SAMPLER_RANDOM,
                   B200PTError, Renderer, detile, load_library)

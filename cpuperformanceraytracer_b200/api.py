@@ -13,7 +13,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libb200pt.so")
 
-PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_OPT_V4 = 0, 1, 2
+PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_OPT_V4, PROFILE_V3_REDO = 0, 1, 2, 3
 MATH_PARITY, MATH_FAST = 0, 1
 ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
 SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2

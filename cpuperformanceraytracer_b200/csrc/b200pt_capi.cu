@@ -22,8 +22,7 @@ struct b200pt_context {
     cudaStream_t stream = nullptr;  // own_stream or a caller-provided one
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
-    CornellScene cornell{};
-    V4Scene v4{};
+    SceneSet scenes{};
     float cameraDistance = 1.f;
 
     // target
@@ -79,7 +78,7 @@ int fail(b200pt_context* ctx, int code, const std::string& msg)
 
 bool uses_env(const b200pt_params& p)
 {
-    if (p.profile == B200PT_PROFILE_SIMT_TEXTURED) return true;
+    if (p.profile == B200PT_PROFILE_SIMT_TEXTURED || p.profile == B200PT_PROFILE_V3_REDO) return true;
     return p.profile == B200PT_PROFILE_OPT_V4 && p.env_kind != B200PT_ENV_NONE;
 }
 
@@ -87,12 +86,12 @@ LaunchConfig launch_config(const b200pt_context* c)
 {
     LaunchConfig lc{};
     lc.profile = c->params.profile;
-    lc.env_kind = c->params.profile == B200PT_PROFILE_SIMT_TEXTURED ? kEnvEquirect
+    lc.env_kind = (c->params.profile == B200PT_PROFILE_SIMT_TEXTURED || c->params.profile == B200PT_PROFILE_V3_REDO) ? kEnvEquirect
                  : c->params.profile == B200PT_PROFILE_V2           ? kEnvNone
                                                                     : c->params.env_kind;
-    lc.env_sampler = c->params.profile == B200PT_PROFILE_OPT_V4 && c->params.env_kind != B200PT_ENV_NONE
-                         ? c->params.env_sampler
-                         : kSamplerPoint;
+    lc.env_sampler = c->params.profile == B200PT_PROFILE_V3_REDO ? kSamplerBilinear
+                     : (c->params.profile == B200PT_PROFILE_OPT_V4 && c->params.env_kind != B200PT_ENV_NONE) ? c->params.env_sampler
+                                                                                                              : kSamplerPoint;
     lc.accum_mode = c->params.accum_mode;
     lc.static_scene = c->params.generic_scene_tables ? 0 : 1;
     lc.block = 256;
@@ -168,7 +167,7 @@ const char* b200pt_last_error(b200pt_context* ctx) { return ctx ? ctx->last_erro
 
 int b200pt_default_params(int profile, b200pt_params* p)
 {
-    if (!p || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_OPT_V4) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!p || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_V3_REDO) return B200PT_ERR_INVALID_ARGUMENT;
     std::memset(p, 0, sizeof(*p));
     p->struct_size = (int32_t)sizeof(b200pt_params);
     p->device = 0;
@@ -183,6 +182,9 @@ int b200pt_default_params(int profile, b200pt_params* p)
     } else if (profile == B200PT_PROFILE_SIMT_TEXTURED) {
         p->env_kind = B200PT_ENV_EQUIRECT;
         p->env_sampler = B200PT_SAMPLER_POINT;
+    } else if (profile == B200PT_PROFILE_V3_REDO) {
+        p->env_kind = B200PT_ENV_EQUIRECT;  // EquirectangularTextureSampleBilinear, v3_redo.cpp:638
+        p->env_sampler = B200PT_SAMPLER_BILINEAR;
     }
     return B200PT_OK;
 }
@@ -192,7 +194,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     if (!params || !out_ctx) return B200PT_ERR_INVALID_ARGUMENT;
     *out_ctx = nullptr;
     if (params->struct_size != (int32_t)sizeof(b200pt_params)) return B200PT_ERR_INVALID_ARGUMENT;
-    if (params->profile < B200PT_PROFILE_V2 || params->profile > B200PT_PROFILE_OPT_V4) return B200PT_ERR_INVALID_ARGUMENT;
+    if (params->profile < B200PT_PROFILE_V2 || params->profile > B200PT_PROFILE_V3_REDO) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->math_mode != B200PT_MATH_PARITY && params->math_mode != B200PT_MATH_FAST) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->accum_mode != B200PT_ACCUM_RUNNING_AVERAGE && params->accum_mode != B200PT_ACCUM_SUM) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->profile == B200PT_PROFILE_OPT_V4) {
@@ -204,7 +206,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     b200pt_context* c = new (std::nothrow) b200pt_context();
     if (!c) return B200PT_ERR_OUT_OF_MEMORY;
     c->params = *params;
-    if (c->params.num_bounces < 0) c->params.num_bounces = (params->profile == B200PT_PROFILE_OPT_V4) ? 8 : 4;
+    if (c->params.num_bounces < 0) c->params.num_bounces = (params->profile == B200PT_PROFILE_OPT_V4 || params->profile == B200PT_PROFILE_V3_REDO) ? 8 : 4;
     c->device = params->device;
 
     int ndev = 0;
@@ -237,8 +239,9 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
 
     // InitializeCamera / InitializeScene (v4.cpp:1403-1502) and the Cornell vertex tables
     c->cameraDistance = camera_distance();
-    build_cornell_scene(&c->cornell, params->profile == B200PT_PROFILE_SIMT_TEXTURED);
-    build_v4_scene(&c->v4);
+    build_cornell_scene(&c->scenes.cornell, params->profile == B200PT_PROFILE_SIMT_TEXTURED);
+    build_v4_scene(&c->scenes.v4);
+    build_v3redo_scene(&c->scenes.v3redo);
 
     LaunchConfig lc = launch_config(c);
     int bps = 0;
@@ -423,8 +426,8 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     CUDA_TRY(c, cudaMemsetAsync(c->d_work_counter, 0, sizeof(int), c->stream));
     CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
     cudaError_t e = (c->params.math_mode == B200PT_MATH_PARITY)
-                        ? launch_render_parity(lc, rp, c->cornell, c->v4, c->stream)
-                        : launch_render_fast(lc, rp, c->cornell, c->v4, c->stream);
+                        ? launch_render_parity(lc, rp, c->scenes, c->stream)
+                        : launch_render_fast(lc, rp, c->scenes, c->stream);
     CUDA_TRY(c, e);
     CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
     c->timing_pending = true;
@@ -629,7 +632,7 @@ int b200pt_download_rng_state(b200pt_context* c, uint32_t* host_dst)
 
 int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float* rects, int32_t* count)
 {
-    if (!rects || !count || width <= 0 || height <= 0 || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_OPT_V4)
+    if (!rects || !count || width <= 0 || height <= 0 || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_V3_REDO)
         return B200PT_ERR_INVALID_ARGUMENT;
     float4 r[kMaxCullRects];
     const int n = compute_cull_rects(profile, width, height, r);

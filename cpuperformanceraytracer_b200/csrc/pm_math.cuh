@@ -114,5 +114,36 @@ __device__ __forceinline__ float asinf_portable(float v)
     return (float)atan2d_portable(x, c);
 }
 
+// exp of a binary32 argument (v3_redo absorption): k = rint(x / ln 2), two-part reduction, degree-13
+// Taylor polynomial, scaling through the exponent field, one rounding to binary32
+__device__ __forceinline__ float expf_portable(float a)
+{
+    double x = (double)a;
+    if (x != x) return __int_as_float(0x7fc00000);
+    if (x > 89.0) return __int_as_float(0x7f800000);
+    if (x < -104.0) return 0.0f;
+    const double LOG2E = 1.44269504088896338700e+00;
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    double kd = rint(__dmul_rn(x, LOG2E));
+    double r = __fma_rn(-kd, LN2_HI, x);
+    r = __fma_rn(-kd, LN2_LO, r);
+    double p = 1.0 / 6227020800.0;
+    p = __fma_rn(r, p, 1.0 / 479001600.0);
+    p = __fma_rn(r, p, 1.0 / 39916800.0);
+    p = __fma_rn(r, p, 1.0 / 3628800.0);
+    p = __fma_rn(r, p, 1.0 / 362880.0);
+    p = __fma_rn(r, p, 1.0 / 40320.0);
+    p = __fma_rn(r, p, 1.0 / 5040.0);
+    p = __fma_rn(r, p, 1.0 / 720.0);
+    p = __fma_rn(r, p, 1.0 / 120.0);
+    p = __fma_rn(r, p, 1.0 / 24.0);
+    p = __fma_rn(r, p, 1.0 / 6.0);
+    p = __fma_rn(r, p, 0.5);
+    p = __fma_rn(r, p, 1.0);
+    p = __fma_rn(r, p, 1.0);
+    const double scale = __longlong_as_double((long long)((long long)kd + 1023) << 52);
+    return __double2float_rn(__dmul_rn(p, scale));
+}
+
 }  // namespace pm
 }  // namespace b200pt

@@ -64,6 +64,27 @@ struct V4Scene {
     float cameraDistance;
 };
 
+// Scene of demofox_path_tracing_v3_redo.cpp, SCENE 1 (:485-600): the v4 geometry tested with the
+// legacy (ScalarTriple) quad test, exact-arithmetic Fresnel materials, a striped backdrop whose
+// albedo is computed at the hit (:511-515), GetZeroedMaterial IOR = 1 for the quads (:155-168).
+constexpr int kV3Quads = 4;
+constexpr int kV3Spheres = 7;
+constexpr int kV3Objects = kV3Quads + kV3Spheres;
+constexpr int kV3BackdropQuad = 1;
+struct V3RedoScene {
+    LegacyQuad quad[kV3Quads];
+    float4 sphere[kV3Spheres];
+    V4Material mat[kV3Objects];
+    v3 cameraPosition;
+};
+// vertex literals of v3_redo.cpp:486-489,505-508,520-523,535-538; the backdrop is not translated
+constexpr float kV3QuadVerts[kV3Quads][4][3] = {
+    {{-25.0f, -12.5f, 5.0f}, {25.0f, -12.5f, 5.0f}, {25.0f, -12.5f, -5.0f}, {-25.0f, -12.5f, -5.0f}},
+    {{-25.0f, -1.5f, 5.0f}, {25.0f, -1.5f, 5.0f}, {25.0f, -10.5f, 5.0f}, {-25.0f, -10.5f, 5.0f}},
+    {{-7.5f, 12.5f, 5.0f}, {7.5f, 12.5f, 5.0f}, {7.5f, 12.5f, -5.0f}, {-7.5f, 12.5f, -5.0f}},
+    {{-5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, -2.5f}, {-5.0f, 12.4f, -2.5f}}};
+constexpr float kV3Translation[kV3Quads][3] = {{0.0f, 0.0f, 10.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 10.0f}, {0.0f, 0.0f, 10.0f}};
+
 constexpr int kMaxCullRects = 12;
 
 struct DeviceCounters {
@@ -99,7 +120,7 @@ struct RenderParams {
     float4 cull_rect[kMaxCullRects];
 };
 
-enum : int { kProfileV2 = 0, kProfileSimtTextured = 1, kProfileV4 = 2 };
+enum : int { kProfileV2 = 0, kProfileSimtTextured = 1, kProfileV4 = 2, kProfileV3Redo = 3 };
 enum : int { kEnvNone = 0, kEnvEquirect = 1, kEnvCubemap = 2 };
 enum : int { kSamplerPoint = 0, kSamplerBilinear = 1, kSamplerRandom = 2 };
 enum : int { kAccumAverage = 0, kAccumSum = 1 };
@@ -111,10 +132,13 @@ struct LaunchConfig {
 };
 
 // implemented in pt_kernels_parity.cu / pt_kernels_fast.cu
-cudaError_t launch_render_parity(const LaunchConfig& lc, const RenderParams& rp, const CornellScene& cs,
-                                 const V4Scene& vs, cudaStream_t stream);
-cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const CornellScene& cs,
-                               const V4Scene& vs, cudaStream_t stream);
+struct SceneSet {
+    CornellScene cornell;
+    V4Scene v4;
+    V3RedoScene v3redo;
+};
+cudaError_t launch_render_parity(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
+cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
 cudaError_t occupancy_parity(const LaunchConfig& lc, int* blocks_per_sm);
 cudaError_t occupancy_fast(const LaunchConfig& lc, int* blocks_per_sm);
 

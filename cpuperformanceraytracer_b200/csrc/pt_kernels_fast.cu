@@ -4,15 +4,16 @@
 
 namespace b200pt {
 
-cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const CornellScene& cs, const V4Scene& vs,
-                               cudaStream_t stream)
+cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream)
 {
     return dispatch_config<FastMath>(lc, [&](auto kernel) -> cudaError_t {
         using KernelT = decltype(kernel);
         if constexpr (std::is_same<KernelT, void (*)(RenderParams, V4Scene)>::value) {
-            kernel<<<lc.grid, lc.block, 0, stream>>>(rp, vs);
+            kernel<<<lc.grid, lc.block, 0, stream>>>(rp, scenes.v4);
+        } else if constexpr (std::is_same<KernelT, void (*)(RenderParams, V3RedoScene)>::value) {
+            kernel<<<lc.grid, lc.block, 0, stream>>>(rp, scenes.v3redo);
         } else {
-            kernel<<<lc.grid, lc.block, 0, stream>>>(rp, cs);
+            kernel<<<lc.grid, lc.block, 0, stream>>>(rp, scenes.cornell);
         }
         return cudaGetLastError();
     });

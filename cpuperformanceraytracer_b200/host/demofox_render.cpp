@@ -12,7 +12,7 @@
 namespace {
 
 B200RenderOptions g_options;
-b200pt_context* g_ctx[3] = {nullptr, nullptr, nullptr};  // one per reference translation unit
+b200pt_context* g_ctx[4] = {nullptr, nullptr, nullptr, nullptr};  // one per reference translation unit
 bool g_tile_data_changed = true;                         // tileDataChanged, v4.cpp:1348
 
 [[noreturn]] void die(const char* what, b200pt_context* ctx, int rc)
@@ -30,7 +30,7 @@ b200pt_context* context_for(int profile)
     if (rc != B200PT_OK) die("b200pt_default_params", nullptr, rc);
     p.device = g_options.device;
     p.math_mode = g_options.math_mode;
-    p.num_bounces = (profile == B200PT_PROFILE_OPT_V4) ? g_options.v4_num_bounces : g_options.v2_num_bounces;
+    p.num_bounces = (profile == B200PT_PROFILE_OPT_V4 || profile == B200PT_PROFILE_V3_REDO) ? g_options.v4_num_bounces : g_options.v2_num_bounces;
     if (profile == B200PT_PROFILE_OPT_V4) {
         p.env_kind = !g_options.use_env_map ? B200PT_ENV_NONE : (g_options.use_env_cubemap ? B200PT_ENV_CUBEMAP : B200PT_ENV_EQUIRECT);
         p.env_sampler = g_options.use_random_jitter_texture_sampling ? B200PT_SAMPLER_RANDOM : B200PT_SAMPLER_BILINEAR;
@@ -97,6 +97,17 @@ void DemofoxRenderSimtTexturedFrames(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 
     render(B200PT_PROFILE_SIMT_TEXTURED, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, NumFrames);
 }
 
+void DemofoxRenderV3Redo(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture)
+{
+    render(B200PT_PROFILE_V3_REDO, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, 1);
+}
+
+void DemofoxRenderV3RedoFrames(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture,
+                               i32 NumFrames)
+{
+    render(B200PT_PROFILE_V3_REDO, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, NumFrames);
+}
+
 // CopyOutputToFile (v4.cpp:1729-1760): tone-maps the f32 buffer into ScreenBufferData
 // (A=FF | B<<16 | G<<8 | R, row-major) and, like the reference, bumps the frame counter.
 void CopyOutputToFile(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture, void* ScreenBufferData)
@@ -159,7 +170,7 @@ void WriteImage(char* filename, i32 width, i32 height, i32 components, void* dat
 B200RenderStats B200GetRenderStats(int variant)
 {
     B200RenderStats s{};
-    if (variant < 0 || variant > 2 || !g_ctx[variant]) return s;
+    if (variant < 0 || variant > 3 || !g_ctx[variant]) return s;
     b200pt_counters c;
     if (b200pt_get_counters(g_ctx[variant], &c) == B200PT_OK) {
         s.last_render_ms = c.last_render_ms;

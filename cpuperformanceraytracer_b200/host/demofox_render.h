@@ -9,6 +9,7 @@
 //   ReinitializeRenderTileData                             demofox_path_tracing_optimization_v4.h:14-26
 //   DemofoxRenderV2                                        demofox_path_tracing_v2.h:8-10
 //   DemofoxRenderSimtTextured                              demofox_path_tracing_simt_textured.h:8-10
+//   DemofoxRenderV3Redo                                    demofox_path_tracing_v3_redo.h
 //   struct texture                                         texture.h:6-12
 //   LoadTexture / LoadCubemapTexture / WriteImage          asset_loading.h
 //
@@ -40,7 +41,7 @@ struct B200RenderOptions {
     int device = 0;
     int math_mode = 0;            // 0 = parity (bit-exact vs the oracle), 1 = fast
     int v2_num_bounces = 4;       // c_numBounces, demofox_path_tracing_v2.cpp:22
-    int v4_num_bounces = 8;       // c_numBounces, demofox_path_tracing_optimization_v4.cpp:23
+    int v4_num_bounces = 8;       // c_numBounces, demofox_path_tracing_optimization_v4.cpp:23 (also v3_redo.cpp:19)
     int use_env_map = USE_ENV_MAP;
     int use_env_cubemap = USE_ENV_CUBEMAP;
     int use_random_jitter_texture_sampling = USE_RANDOM_JITTER_TEXTURE_SAMPLING;
@@ -61,6 +62,9 @@ void DemofoxRenderV2(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumT
 void DemofoxRenderSimtTextured(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
                                i32 TileHeight, i32 NumChannels, texture Texture);
 
+void DemofoxRenderV3Redo(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                         i32 TileHeight, i32 NumChannels, texture Texture);
+
 // ---- batched forms: NumFrames consecutive calls of the entry point above in ONE kernel launch and
 // ---- one host<->device round trip (what RenderOffline's frame loop amounts to, Application.cpp:426-438)
 void DemofoxRenderOptV4Frames(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
@@ -69,6 +73,9 @@ void DemofoxRenderV2Frames(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i3
                            i32 TileHeight, i32 NumChannels, texture Texture, i32 NumFrames);
 void DemofoxRenderSimtTexturedFrames(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY,
                                      i32 TileWidth, i32 TileHeight, i32 NumChannels, texture Texture, i32 NumFrames);
+
+void DemofoxRenderV3RedoFrames(f32* BufferOut, i32 BufferWidth, i32 BufferHeight, i32 NumTilesX, i32 NumTilesY, i32 TileWidth,
+                               i32 TileHeight, i32 NumChannels, texture Texture, i32 NumFrames);
 
 // ---- asset_loading.h ---------------------------------------------------------------------------------
 texture LoadTexture(char* filename);
@@ -80,4 +87,4 @@ struct B200RenderStats {
     double last_render_ms;
     u64 paths, segments, escapes, launches;
 };
-B200RenderStats B200GetRenderStats(int variant /*0 = v2, 1 = simt_textured, 2 = opt_v4*/);
+B200RenderStats B200GetRenderStats(int variant /*0 = v2, 1 = simt_textured, 2 = opt_v4, 3 = v3_redo*/);

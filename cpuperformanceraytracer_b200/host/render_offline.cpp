@@ -4,7 +4,7 @@
 // ms/frame (:444-452), tone-map and write output_image.bmp (PostprocessAndWriteImageToFile, :381-398).
 // It is written against the reference's own entry-point names (demofox_render.h).
 //
-//   render_offline [--variant v4|v2|simt] [--width W --height H --tiles-x X --tiles-y Y]
+//   render_offline [--variant v4|v2|simt|v3redo] [--width W --height H --tiles-x X --tiles-y Y]
 //                  [--frames N] [--bounces B] [--env file.hdr | --cubemap px nx py ny pz nz]
 //                  [--bilinear] [--fast] [--per-frame-calls] [--out out.bmp] [--dump-f32 file]
 #include <chrono>
@@ -52,10 +52,10 @@ int main(int argc, char** argv)
     texture Texture;
     if (cube[0]) Texture = LoadCubemapTexture(cube);
     else if (!env_path.empty()) Texture = LoadTexture((char*)env_path.c_str());
-    const bool needs_env = (variant == "simt") || (variant == "v4");
+    const bool needs_env = (variant == "simt") || (variant == "v4") || (variant == "v3redo");
     if (needs_env && !Texture.Data) {
         if (variant == "v4") opt.use_env_map = 0;  // no texture given: constant ambient
-        else { std::fprintf(stderr, "--variant simt needs --env file.hdr\n"); return 2; }
+        else { std::fprintf(stderr, "--variant %s needs --env file.hdr\n", variant.c_str()); return 2; }
     }
     B200SetRenderOptions(opt);
 
@@ -69,19 +69,22 @@ int main(int argc, char** argv)
         } else if (variant == "v2") {
             if (per_frame_calls) for (int f = 0; f < n; f++) DemofoxRenderV2(RenderTarget.data(), W, H, ntx, nty, TW, TH, 3, Texture);
             else DemofoxRenderV2Frames(RenderTarget.data(), W, H, ntx, nty, TW, TH, 3, Texture, n);
+        } else if (variant == "v3redo") {
+            if (per_frame_calls) for (int f = 0; f < n; f++) DemofoxRenderV3Redo(RenderTarget.data(), W, H, ntx, nty, TW, TH, 3, Texture);
+            else DemofoxRenderV3RedoFrames(RenderTarget.data(), W, H, ntx, nty, TW, TH, 3, Texture, n);
         } else {
             if (per_frame_calls) for (int f = 0; f < n; f++) DemofoxRenderSimtTextured(RenderTarget.data(), W, H, ntx, nty, TW, TH, 3, Texture);
             else DemofoxRenderSimtTexturedFrames(RenderTarget.data(), W, H, ntx, nty, TW, TH, 3, Texture, n);
         }
     };
-    if (variant != "v4" && variant != "v2" && variant != "simt") { std::fprintf(stderr, "unknown variant\n"); return 2; }
+    if (variant != "v4" && variant != "v2" && variant != "simt" && variant != "v3redo") { std::fprintf(stderr, "unknown variant\n"); return 2; }
 
     Render(2);  // two warm-up frames (they accumulate), Application.cpp:421-422
     const auto t0 = std::chrono::steady_clock::now();
     Render(frames);
     const auto t1 = std::chrono::steady_clock::now();
     const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
-    const B200RenderStats st = B200GetRenderStats(variant == "v2" ? 0 : variant == "simt" ? 1 : 2);
+    const B200RenderStats st = B200GetRenderStats(variant == "v2" ? 0 : variant == "simt" ? 1 : variant == "v3redo" ? 3 : 2);
     std::printf("Total render time: %.3f ms, average frame time: %.5f ms (%d frames, %dx%d, %.1f Mpaths/s wall; "
                 "last kernel %.3f ms on device)\n", ms, ms / frames, frames, W, H, (double)W * H * frames / ms * 1e-3,
                 st.last_render_ms);

@@ -127,6 +127,40 @@ void build_v4_scene(V4Scene* s)
     s->cameraPosition = mk(0.f, 0.f, 1.f * 40.f);  // v4.cpp:1501
 }
 
+// Scene of demofox_path_tracing_v3_redo.cpp, SCENE 1 (:485-600)
+void build_v3redo_scene(V3RedoScene* s)
+{
+    std::memset(s, 0, sizeof(*s));
+    for (int i = 0; i < kV3Quads; i++) {
+        LegacyQuad& q = s->quad[i];
+        const v3 T = mk(kV3Translation[i][0], kV3Translation[i][1], kV3Translation[i][2]);
+        v3* dst[4] = {&q.a, &q.b, &q.c, &q.d};
+        for (int k = 0; k < 4; k++) {
+            const v3 p = mk(kV3QuadVerts[i][k][0], kV3QuadVerts[i][k][1], kV3QuadVerts[i][k][2]);
+            *dst[k] = (i == kV3BackdropQuad) ? p : add(p, T);  // the backdrop literals are used untranslated (:505-508)
+        }
+        q.n = normalize(cross(sub(q.c, q.a), sub(q.c, q.b)));  // :225
+    }
+    for (int i = 0; i < kV3Objects; i++) s->mat[i].IOR = 1.f;  // GetZeroedMaterial, :155-168
+    s->mat[0].albedo = mk(0.7f, 0.7f, 0.7f);
+    s->mat[2].albedo = mk(0.7f, 0.7f, 0.7f);
+    s->mat[3].emissive = muls(mk(1.0f, 0.9f, 0.7f), 20.0f);
+    for (int i = 0; i < kV3Spheres; i++) {  // :575-598
+        const v3 c = add(mk(-18.0f + 6.0f * (float)i, -8.0f, 0.0f), mk(0.0f, 0.0f, 10.0f));
+        s->sphere[i] = make_float4(c.x, c.y, c.z, 2.8f + 0.0f);
+        V4Material& m = s->mat[kV3Quads + i];
+        const float r = ((float)i / (float)(kV3Spheres - 1)) * 0.5f;
+        m.albedo = mk(0.9f, 0.25f, 0.25f);
+        m.specularChance = 0.02f;
+        m.specularRoughness = r;
+        m.specularColor = muls(mk(1.0f, 1.0f, 1.0f), 0.8f);
+        m.IOR = 1.1f;
+        m.refractionChance = 1.0f;
+        m.refractionRoughness = r;
+        m.refractionColor = mk(0.0f, 0.5f, 1.0f);
+    }
+    s->cameraPosition = mk(0.f, 0.f, 1.f * 40.f);  // :796
+}
 
 // ---- camera-ray culling ---------------------------------------------------------------------------
 // A camera ray through fragCoord (fx, fy) has direction (tx, ty / aspect, camDist) with
@@ -192,7 +226,7 @@ int compute_cull_rects(int profile, int width, int height, float4* rects)
 {
     const double camDist = camera_distance();
     int n = 0;
-    if (profile == kProfileV4) {
+    if (profile == kProfileV4 || profile == kProfileV3Redo) {  // same geometry, same camera model
         V4Scene s;
         build_v4_scene(&s);
         // the quad table only keeps V0 and edge bivectors; rebuild the vertex boxes from the source data
@@ -204,10 +238,10 @@ int compute_cull_rects(int profile, int width, int height, float4* rects)
         for (int i = 0; i < kV4Quads; i++) {
             Box b;
             for (int a = 0; a < 3; a++) { b.lo[a] = q[i][0][a] - 1e-3; b.hi[a] = q[i][1][a] + 1e-3; }
-            if (!project_box(b, profile, width, height, camDist, &rects[n++])) return -1;
+            if (!project_box(b, kProfileV4, width, height, camDist, &rects[n++])) return -1;
         }
         for (int i = 0; i < kV4Spheres; i++)
-            if (!project_box(sphere_box(s.sphere[i]), profile, width, height, camDist, &rects[n++])) return -1;
+            if (!project_box(sphere_box(s.sphere[i]), kProfileV4, width, height, camDist, &rects[n++])) return -1;
     } else {
         CornellScene s;
         build_cornell_scene(&s, profile == kProfileSimtTextured);

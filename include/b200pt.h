@@ -41,8 +41,11 @@ enum {
                                          diffuse/emissive/specular, jitter, constant ambient) */
     B200PT_PROFILE_SIMT_TEXTURED = 1, /* DemofoxRenderSimtTextured, ..._simt_textured.cpp:560 (Cornell,
                                          diffuse/emissive, equirect point-sampled env) */
-    B200PT_PROFILE_OPT_V4 = 2         /* DemofoxRenderOptV4, ..._optimization_v4.cpp:1696 (7 spheres,
+    B200PT_PROFILE_OPT_V4 = 2,        /* DemofoxRenderOptV4, ..._optimization_v4.cpp:1696 (7 spheres,
                                          Fresnel/refraction/absorption, equirect or cubemap env) */
+    B200PT_PROFILE_V3_REDO = 3        /* DemofoxRenderV3Redo, demofox_path_tracing_v3_redo.cpp:886, SCENE 1: the v4
+                                         scene and shading without the approximations (exact divisions, exp(),
+                                         sin/cos unit vectors, striped backdrop), bilinear equirect env, 8 bounces */
 };
 
 /* arithmetic policy */

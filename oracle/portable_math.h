@@ -137,6 +137,39 @@ static inline float pm_asinf(float v)
     return (float)pm_atan2d(x, c);
 }
 
+/* exp of a binary32 argument (v3_redo absorption, demofox_path_tracing_v3_redo.cpp:649-651):
+ * k = rint(x / ln 2), r = x - k ln 2 (two-part ln 2), degree-13 Taylor polynomial of exp(r),
+ * |r| <= 0.347, scaled by 2^k through the exponent field, rounded once to binary32. */
+static inline float pm_expf(float a)
+{
+    double x = (double)a;
+    if (x != x) return NAN;
+    if (x > 89.0) return INFINITY;
+    if (x < -104.0) return 0.0f;
+    const double LOG2E = 1.44269504088896338700e+00;
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    double kd = __builtin_rint(x * LOG2E);
+    double r = PM_FMA(-kd, LN2_HI, x);
+    r = PM_FMA(-kd, LN2_LO, r);
+    double p = 1.0 / 6227020800.0; /* 1/13! */
+    p = PM_FMA(r, p, 1.0 / 479001600.0);
+    p = PM_FMA(r, p, 1.0 / 39916800.0);
+    p = PM_FMA(r, p, 1.0 / 3628800.0);
+    p = PM_FMA(r, p, 1.0 / 362880.0);
+    p = PM_FMA(r, p, 1.0 / 40320.0);
+    p = PM_FMA(r, p, 1.0 / 5040.0);
+    p = PM_FMA(r, p, 1.0 / 720.0);
+    p = PM_FMA(r, p, 1.0 / 120.0);
+    p = PM_FMA(r, p, 1.0 / 24.0);
+    p = PM_FMA(r, p, 1.0 / 6.0);
+    p = PM_FMA(r, p, 0.5);
+    p = PM_FMA(r, p, 1.0);
+    p = PM_FMA(r, p, 1.0);
+    union { uint64_t u; double d; } scale;
+    scale.u = (uint64_t)((int64_t)kd + 1023) << 52;
+    return (float)(p * scale.d);
+}
+
 #ifdef __cplusplus
 }
 #endif

@@ -153,6 +153,7 @@ static int TestQuadTrace_legacy(v3 rayPos, v3 rayDir, hit_t* info, v3 a, v3 b, v
     if (fabsf(rayDir.y) > 0.f) dist = (intersectPos.y - rayPos.y) / rayDir.y;
     if (fabsf(rayDir.x) > 0.f) dist = (intersectPos.x - rayPos.x) / rayDir.x;
     if (!early_return && dist > c_minimumRayHitTime && dist < info->dist) {
+        info->fromInside = 0; /* v3_redo.cpp:305 (the v2 struct has no such field) */
         info->dist = dist;
         info->normal = normal;
         return 1;
@@ -173,6 +174,7 @@ static int TestSphereTrace_legacy(v3 rayPos, v3 rayDir, hit_t* info, v3 center, 
     int fromInside = dist < 0.f;
     if (fromInside) dist = -b + sq;
     if (!early_return && dist > c_minimumRayHitTime && dist < info->dist) {
+        info->fromInside = fromInside; /* v3_redo.cpp:366 */
         info->dist = dist;
         v3 n = normalize3(sub3(add3(rayPos, muls(rayDir, dist)), center));
         info->normal = muls(n, fromInside ? -1.0f : 1.0f);
@@ -525,11 +527,54 @@ static v3 RandomUnitVectorRejectionSample(uint32_t* state)
     return muls(V3(u, v, w), rsroot_exact(uvw_d2));
 }
 
+/* ---- v3_redo, SCENE 1: v3_redo.cpp:195-219 (Fresnel), :485-600 (scene), :607-754 (shading) ---- */
+typedef struct {
+    v3 quad[4][4];
+    v3 sphereCenter[7];
+    float sphereRadius[7];
+    mat4_t mat[11]; /* [1] (striped backdrop) albedo is computed at the hit */
+} scene3_t;
+
+static void scene3_init(scene3_t* s)
+{
+    const v3 T = V3(0.0f, 0.0f, 10.0f);
+    memset(s, 0, sizeof(*s));
+    static const float Q[4][4][3] = {
+        {{-25.0f, -12.5f, 5.0f}, {25.0f, -12.5f, 5.0f}, {25.0f, -12.5f, -5.0f}, {-25.0f, -12.5f, -5.0f}},
+        {{-25.0f, -1.5f, 5.0f}, {25.0f, -1.5f, 5.0f}, {25.0f, -10.5f, 5.0f}, {-25.0f, -10.5f, 5.0f}},
+        {{-7.5f, 12.5f, 5.0f}, {7.5f, 12.5f, 5.0f}, {7.5f, 12.5f, -5.0f}, {-7.5f, 12.5f, -5.0f}},
+        {{-5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, -2.5f}, {-5.0f, 12.4f, -2.5f}}};
+    for (int i = 0; i < 4; i++)
+        for (int k = 0; k < 4; k++) {
+            v3 p = V3(Q[i][k][0], Q[i][k][1], Q[i][k][2]);
+            s->quad[i][k] = (i == 1) ? p : add3(p, T); /* the backdrop is not translated, :505-508 */
+        }
+    for (int i = 0; i < 11; i++) s->mat[i].IOR = 1.f; /* GetZeroedMaterial, :155-168 */
+    s->mat[0].albedo = V3(0.7f, 0.7f, 0.7f);
+    s->mat[2].albedo = V3(0.7f, 0.7f, 0.7f);
+    s->mat[3].emissive = muls(V3(1.0f, 0.9f, 0.7f), 20.0f);
+    for (int i = 0; i < 7; i++) {
+        s->sphereCenter[i] = add3(V3(-18.0f + 6.0f * (float)i, -8.0f, 0.0f), T);
+        s->sphereRadius[i] = 2.8f + 0.0f;
+        mat4_t* m = &s->mat[4 + i];
+        float r = ((float)i / (float)(7 - 1)) * 0.5f;
+        m->albedo = V3(0.9f, 0.25f, 0.25f);
+        m->specularChance = 0.02f;
+        m->specularRoughness = r;
+        m->specularColor = muls(V3(1.0f, 1.0f, 1.0f), 0.8f);
+        m->IOR = 1.1f;
+        m->refractionChance = 1.0f;
+        m->refractionRoughness = r;
+        m->refractionColor = V3(0.0f, 0.5f, 1.0f);
+    }
+}
+
 /* ---- per-path radiance --------------------------------------------------------------------- */
 typedef struct {
     const oracle_params* p;
     cornell_t cornell;
     scene4_t scene4;
+    scene3_t scene3;
     tex_t tex;
 } ctx_t;
 
@@ -683,6 +728,106 @@ static v3 GetColorForRay_v4(const ctx_t* c, v3 rayPos, v3 rayDir, uint32_t* rng,
     return ret;
 }
 
+/* v3_redo.cpp:195-219: exact divisions, no fused operations */
+static float FresnelReflectAmount_v3(float n1, float n2, v3 normal, v3 incident, float f0, float f90)
+{
+    float r0 = (n1 - n2) / (n1 + n2);
+    r0 = r0 * r0;
+    float cosX = -dot3(normal, incident);
+    int cond = n1 > n2;
+    float n = n1 / n2;
+    float sinT2 = n * n * (1.f - cosX * cosX);
+    float newCosX = sqrtf(1.f - sinT2);
+    int tir = sinT2 > 1.f;
+    if (cond && !tir) cosX = newCosX;
+    float x = 1.f - cosX;
+    float x2 = x * x;
+    float ret = r0 + (1.f - r0) * x2 * x2 * x;
+    if (cond && tir) ret = 1.f;
+    return f0 + ret * (f90 - f0);
+}
+
+static v3 GetColorForRay_v3redo(const scene3_t* s, const oracle_params* p, const tex_t* tex, v3 rayPos, v3 rayDir,
+                                uint32_t* rng, path_stats_t* st)
+{
+    v3 ret = V3(0.f, 0.f, 0.f), throughput = V3(1.f, 1.f, 1.f);
+    for (int bounceIndex = 0; bounceIndex <= p->num_bounces; ++bounceIndex) {
+        hit_t h;
+        h.fromInside = 0; h.dist = c_superFar; h.normal = V3(0.f, 0.f, 0.f); h.matIndex = -1;
+        v3 backdropAlbedo = V3(0.f, 0.f, 0.f);
+        st->segments++;
+        for (int i = 0; i < 4; i++)
+            if (TestQuadTrace_legacy(rayPos, rayDir, &h, s->quad[i][0], s->quad[i][1], s->quad[i][2], s->quad[i][3])) {
+                h.matIndex = i;
+                if (i == 1) { /* striped backdrop, :511-515 */
+                    v3 hitPos = add3(rayPos, muls(rayDir, h.dist));
+                    float shade = floorf(fract1(hitPos.x) * 2.0f);
+                    backdropAlbedo = V3(shade, shade, shade);
+                }
+            }
+        for (int i = 0; i < 7; i++)
+            if (TestSphereTrace_legacy(rayPos, rayDir, &h, s->sphereCenter[i], s->sphereRadius[i])) h.matIndex = 4 + i;
+        if (h.dist == c_superFar) {
+            v3 SampleDir = V3(-rayDir.x, rayDir.y, -rayDir.z);
+            v3 ambient = mul3(EquirectSampleBilinear(tex, SampleDir), throughput);
+            st->escapes++;
+            return add3(ret, ambient);
+        }
+        mat4_t m = s->mat[h.matIndex];
+        if (h.matIndex == 1) m.albedo = backdropAlbedo;
+        if (h.fromInside) {
+            throughput.x = throughput.x * pm_expf(-m.refractionColor.x * h.dist);
+            throughput.y = throughput.y * pm_expf(-m.refractionColor.y * h.dist);
+            throughput.z = throughput.z * pm_expf(-m.refractionColor.z * h.dist);
+        }
+        float specularChance = m.specularChance, refractionChance = m.refractionChance;
+        {
+            int hasSpecularChance = specularChance > 0.f;
+            float n1 = h.fromInside ? m.IOR : 1.f, n2 = h.fromInside ? 1.f : m.IOR;
+            float newSpecularChance = FresnelReflectAmount_v3(n1, n2, h.normal, rayDir, m.specularChance, 1.f);
+            float chanceMultiplier = (1.f - newSpecularChance) / (1.f - m.specularChance);
+            if (hasSpecularChance) {
+                specularChance = newSpecularChance;
+                refractionChance = refractionChance * chanceMultiplier;
+            }
+        }
+        float raySelectRoll = RAND01(rng);
+        int doSpecular = (specularChance > 0.f) && (raySelectRoll < specularChance);
+        int doRefraction = (!doSpecular) && (refractionChance > 0.f) && (raySelectRoll < (specularChance + refractionChance));
+        int doDiffuse = (!doSpecular) && (!doRefraction);
+        float diffuseChance = max_ps(1.f - (specularChance + refractionChance), 0.f);
+        float rayProbability = 1.f;
+        if (doSpecular) rayProbability = specularChance;
+        if (doRefraction) rayProbability = refractionChance;
+        if (doDiffuse) rayProbability = diffuseChance;
+        rayProbability = max_ps(rayProbability, 1.f * 0.001f);
+        float doRefractionSign = doRefraction ? -1.f : 1.f;
+        v3 newRayPos = add3(rayPos, add3(muls(rayDir, h.dist), muls(muls(h.normal, doRefractionSign), c_rayPosNormalNudge)));
+        v3 diffuseRayDir = normalize3(add3(h.normal, RandomUnitVector(rng)));
+        v3 specularRayDir = sub3(rayDir, muls(muls(h.normal, 2.f), dot3(rayDir, h.normal)));
+        float specularRoughnessSqrd = m.specularRoughness * m.specularRoughness;
+        specularRayDir = normalize3(lerp3(specularRayDir, diffuseRayDir, specularRoughnessSqrd));
+        float IOR = h.fromInside ? m.IOR : 1.0f / m.IOR;
+        float refractionRoughnessSquared = m.refractionRoughness * m.refractionRoughness;
+        v3 refractionRayDir = rfrct(rayDir, h.normal, IOR);
+        refractionRayDir = normalize3(lerp3(refractionRayDir, normalize3(sub3(RandomUnitVector(rng), h.normal)), refractionRoughnessSquared));
+        v3 newRayDir = doSpecular ? specularRayDir : diffuseRayDir;
+        if (doRefraction) newRayDir = refractionRayDir;
+        ret = add3(ret, mul3(m.emissive, throughput));
+        v3 colorFactor = doSpecular ? m.specularColor : m.albedo;
+        if (!doRefraction) throughput = mul3(throughput, colorFactor);
+        throughput = V3(throughput.x / rayProbability, throughput.y / rayProbability, throughput.z / rayProbability);
+        {
+            float pmax = max_ps(throughput.x, max_ps(throughput.y, throughput.z));
+            int rouletteTermination = RAND01(rng) > pmax;
+            if (!rouletteTermination) throughput = muls(throughput, 1.0f / pmax);
+        }
+        rayPos = newRayPos;
+        rayDir = newRayDir;
+    }
+    return ret;
+}
+
 /* mainImage: v2.cpp:526-568, simt_textured.cpp:433-474, v4.cpp:1092-1131 */
 static v3 mainImage(const ctx_t* c, int x, int yflip, int frame, uint32_t* rng_out, path_stats_t* st)
 {
@@ -705,7 +850,7 @@ static v3 mainImage(const ctx_t* c, int x, int yflip, int frame, uint32_t* rng_o
     } else {
         float cameraDistance = oracle_camera_distance();
         float tx, ty;
-        if (p->profile == ORACLE_PROFILE_V2) {
+        if (p->profile == ORACLE_PROFILE_V2 || p->profile == ORACLE_PROFILE_V3REDO) {
             float jx = RAND01(&rng) - .5f;
             float jy = RAND01(&rng) - .5f;
             tx = ((fx + jx) / resx) * 2.0f - 1.f;
@@ -719,8 +864,13 @@ static v3 mainImage(const ctx_t* c, int x, int yflip, int frame, uint32_t* rng_o
         rayTarget.y = rayTarget.y / aspectRatio;
         v3 rayPosition = V3(0.f, 0.f, 0.f);
         v3 rayDir = normalize3(sub3(rayTarget, rayPosition));
-        v3 col = (p->profile == ORACLE_PROFILE_V2) ? GetColorForRay_v2(c, rayPosition, rayDir, &rng, st)
-                                                   : GetColorForRay_simt_textured(c, rayPosition, rayDir, &rng, st);
+        v3 col;
+        if (p->profile == ORACLE_PROFILE_V3REDO) { /* v3_redo.cpp:791-798: camera at (0,0,40) looking down -z */
+            rayDir.z = rayDir.z * -1.f;
+            col = GetColorForRay_v3redo(&c->scene3, p, &c->tex, V3(0.f, 0.f, 1.f * 40.f), rayDir, &rng, st);
+        } else
+            col = (p->profile == ORACLE_PROFILE_V2) ? GetColorForRay_v2(c, rayPosition, rayDir, &rng, st)
+                                                    : GetColorForRay_simt_textured(c, rayPosition, rayDir, &rng, st);
         color = add3(V3(0.f, 0.f, 0.f), muls(col, 1.f / 1));
     }
     if (rng_out) *rng_out = rng;
@@ -731,13 +881,14 @@ static int ctx_init(ctx_t* c, const oracle_params* p)
 {
     if (!p || p->width <= 0 || p->height <= 0 || p->num_tiles_x <= 0 || p->num_tiles_y <= 0) return -1;
     if (p->width % p->num_tiles_x || p->height % p->num_tiles_y || (p->width / p->num_tiles_x) % 8) return -1;
-    if (p->profile < 0 || p->profile > 2 || p->num_bounces < 0) return -1;
-    int needs_env = (p->profile == ORACLE_PROFILE_SIMT_TEXTURED) ||
+    if (p->profile < 0 || p->profile > 3 || p->num_bounces < 0) return -1;
+    int needs_env = (p->profile == ORACLE_PROFILE_SIMT_TEXTURED) || (p->profile == ORACLE_PROFILE_V3REDO) ||
                     (p->profile == ORACLE_PROFILE_V4 && p->env_kind != ORACLE_ENV_NONE);
     if (needs_env && (!p->env || p->env_width <= 0 || p->env_height <= 0)) return -1;
     c->p = p;
     cornell_init(&c->cornell, p->profile);
     scene4_init(&c->scene4);
+    scene3_init(&c->scene3);
     c->tex.data = p->env; c->tex.W = p->env_width; c->tex.H = p->env_height;
     return 0;
 }
@@ -911,4 +1062,8 @@ int oracle_max_segments(const oracle_params* p, int first_frame, int nframes, ui
             out[(size_t)y * p->width + x] = mx;
         }
     return 0;
+}
+void oracle_pm_expf_array(const float* x, float* out, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = pm_expf(x[i]);
 }

@@ -59,6 +59,7 @@ for mode in exact asis; do
     build_variant "ref_simt_textured_$mode" 2 demofox_path_tracing_simt_textured.cpp "$mode" &
     build_variant "ref_v4_equirect_random_$mode" 3 demofox_path_tracing_optimization_v4.cpp "$mode" $V4_EQ_RAND &
     build_variant "ref_v4_cubemap_random_$mode" 3 demofox_path_tracing_optimization_v4.cpp "$mode" $V4_CUBE_RAND &
+    build_variant "ref_v3redo_$mode" 4 demofox_path_tracing_v3_redo.cpp "$mode" &
     for j in $(jobs -p); do wait "$j"; done
 done
 build_variant ref_v4_equirect_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_BILIN &

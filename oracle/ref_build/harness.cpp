@@ -7,6 +7,7 @@
  *
  *   -DORACLE_VARIANT=1  DemofoxRenderV2            (demofox_path_tracing_v2.h:8-10)
  *   -DORACLE_VARIANT=2  DemofoxRenderSimtTextured  (demofox_path_tracing_simt_textured.h:8-10)
+ *   -DORACLE_VARIANT=4  DemofoxRenderV3Redo        (demofox_path_tracing_v3_redo.h)
  *   -DORACLE_VARIANT=3  DemofoxRenderOptV4 (+ CopyOutputToFile)
  *                       (demofox_path_tracing_optimization_v4.h:14-26)
  *
@@ -37,8 +38,11 @@ void DemofoxRenderOptV4(f32*, i32, i32, i32, i32, i32, i32, i32, texture, void*)
 void CopyOutputToFile(f32*, i32, i32, i32, i32, i32, i32, i32, texture, void*);
 void InitializeGlobalRenderResources();
 #define ORACLE_RENDER(buf, W, H, ntx, nty, tw, th, tex, scr) DemofoxRenderOptV4(buf, W, H, ntx, nty, tw, th, 3, tex, scr)
+#elif ORACLE_VARIANT == 4
+void DemofoxRenderV3Redo(f32*, i32, i32, i32, i32, i32, i32, i32, texture);
+#define ORACLE_RENDER(buf, W, H, ntx, nty, tw, th, tex, scr) DemofoxRenderV3Redo(buf, W, H, ntx, nty, tw, th, 3, tex)
 #else
-#error "ORACLE_VARIANT must be 1, 2 or 3"
+#error "ORACLE_VARIANT must be 1, 2, 3 or 4"
 #endif
 
 static bool read_file(const char* path, void* dst, size_t bytes)

@@ -75,16 +75,17 @@ ORACLE_LANEWISE1(_mm256_sin_ps, pm_sinf(x))
 ORACLE_LANEWISE1(_mm256_cos_ps, pm_cosf(x))
 ORACLE_LANEWISE1(_mm256_asin_ps, pm_asinf(x))
 ORACLE_LANEWISE2(_mm256_atan2_ps, pm_atan2f(x, y))
+ORACLE_LANEWISE1(_mm256_exp_ps, pm_expf(x))
 #else
 ORACLE_LANEWISE1(_mm256_sin_ps, sinf(x))
 ORACLE_LANEWISE1(_mm256_cos_ps, cosf(x))
 ORACLE_LANEWISE1(_mm256_asin_ps, asinf(x))
 ORACLE_LANEWISE2(_mm256_atan2_ps, atan2f(x, y))
+ORACLE_LANEWISE1(_mm256_exp_ps, expf(x))
 #endif
 ORACLE_LANEWISE1(_mm256_tan_ps, tanf(x))
 ORACLE_LANEWISE1(_mm256_acos_ps, acosf(x))
 ORACLE_LANEWISE1(_mm256_atan_ps, atanf(x))
-ORACLE_LANEWISE1(_mm256_exp_ps, expf(x))
 ORACLE_LANEWISE1(_mm256_log_ps, logf(x))
 ORACLE_LANEWISE2(_mm256_pow_ps, powf(x, y))
 

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 from cpuperformanceraytracer_b200 import api  # noqa: E402
 
-GPU_PROFILE = {0: api.PROFILE_V2, 1: api.PROFILE_SIMT_TEXTURED, 2: api.PROFILE_OPT_V4}
+GPU_PROFILE = {0: api.PROFILE_V2, 1: api.PROFILE_SIMT_TEXTURED, 2: api.PROFILE_OPT_V4, 3: api.PROFILE_V3_REDO}
 
 
 def make_renderer(case_profile, bounces, env_kind, env_sampler, math_mode=api.MATH_PARITY, **kw):
@@ -49,6 +49,7 @@ CONFIGS = [
     ("v4_cubemap_random", 2, (64, 384), 2, 2, 8),
     ("v4_cubemap_bilinear", 2, (64, 384), 2, 1, 8),
     ("v4_no_env", 2, None, 0, 0, 8),
+    ("v3_redo", 3, (256, 128), 1, 1, 8),
 ]
 
 
@@ -201,8 +202,9 @@ def test_full_size_properties():
 
 
 @pytest.mark.parametrize("profile,envshape,ek,es", [(api.PROFILE_V2, None, None, None), (api.PROFILE_OPT_V4, (128, 64), 1, 2),
-                                                    (api.PROFILE_SIMT_TEXTURED, (128, 64), None, None)],
-                         ids=["v2", "v4", "simt_textured"])
+                                                    (api.PROFILE_SIMT_TEXTURED, (128, 64), None, None),
+                                                    (api.PROFILE_V3_REDO, (128, 64), None, None)],
+                         ids=["v2", "v4", "simt_textured", "v3_redo"])
 def test_camera_culling_changes_nothing(oracle, profile, envshape, ek, es):
     """Skipping the scene trace for pixels whose jitter footprint misses every primitive's screen
     bounds must not change a single bit (buffer, RNG states, counters)."""
@@ -237,11 +239,12 @@ def test_tile_row_bands_assemble_to_the_full_render(oracle):
             r.set_tile_row_range(4, 2)
 
 
-@pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED], ids=["v2", "simt_textured"])
+@pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_V3_REDO],
+                         ids=["v2", "simt_textured", "v3_redo"])
 def test_static_scene_specialisation_changes_nothing(oracle, profile):
-    """Cornell vertices as immediates (default) vs read from the scene table: identical bits."""
+    """Quad vertices as immediates (default) vs read from the scene table: identical bits."""
     W, H, ntx, nty, frames = 256, 160, 4, 5, 10
-    env = oracle.synthetic_env(128, 64) if profile == api.PROFILE_SIMT_TEXTURED else None
+    env = oracle.synthetic_env(128, 64) if profile != api.PROFILE_V2 else None
     res = []
     for generic in (False, True):
         with api.Renderer(profile=profile, num_bounces=8, generic_scene_tables=generic) as r:

@@ -45,6 +45,17 @@ def test_v4(oracle, name, kind, sampler, envshape):
 
 
 @needs_ref
+@pytest.mark.parametrize("bounces,frames,tiles", [(8, 4, (2, 4)), (16, 2, (4, 2))])
+def test_v3_redo(oracle, bounces, frames, tiles):
+    W, H = 256, 144
+    env = po.synthetic_env(256, 128)
+    o, _ = oracle.render(po.PROFILE_V3REDO, W, H, tiles[0], tiles[1], bounces, frames, env=env, env_kind=po.ENV_EQUIRECT,
+                         env_sampler=po.SAMPLER_BILINEAR)
+    r = po.run_ref("ref_v3redo_exact", W, H, tiles[0], tiles[1], frames, bounces=bounces, env=env)["buffer"]
+    assert np.array_equal(o, r)
+
+
+@needs_ref
 @pytest.mark.skipif(not os.path.exists(os.path.join(TEX_DIR, "HDR_040_Field_Env.hdr")), reason="reference textures absent")
 def test_v4_real_textures(oracle, tmp_path):
     """The reference's shipped HDR env maps, decoded by the reference's own loader (stb_image)."""

@@ -64,3 +64,19 @@ def test_edge_cases(oracle):
     assert L.oracle_pm_atan2f(1.0, 0.0) == np.float32(np.pi / 2)
     assert np.isnan(L.oracle_pm_asinf(1.0000001))  # normalised directions can overshoot 1 by an ulp
     assert L.oracle_pm_asinf(-1.0) == -np.float32(np.pi / 2)
+
+
+def test_expf(oracle):
+    L = oracle.lib()
+    L.oracle_pm_expf_array.argtypes = [ctypes.POINTER(ctypes.c_float), ctypes.POINTER(ctypes.c_float), ctypes.c_int64]
+    rng = np.random.default_rng(4)
+    x = np.concatenate([-rng.uniform(0, 60, 1_000_000), rng.uniform(0, 5, 100_000)]).astype(np.float32)  # absorption: -colour * dist
+    out = np.empty_like(x)
+    L.oracle_pm_expf_array(_fp(x), _fp(out), x.size)
+    ref = np.exp(x.astype(np.float64)).astype(np.float32)
+    assert _ulp_diff(out, ref).max() <= 1 and (out == ref).mean() > 0.9999
+    assert _ulp_diff(out, np.exp(x)).max() <= 2  # numpy's vectorised float32 exp is itself only faithful to ~2 ulp
+    e = np.array([0.0, -200.0, 100.0, -103.0], dtype=np.float32)
+    o = np.empty_like(e)
+    L.oracle_pm_expf_array(_fp(e), _fp(o), e.size)
+    assert o[0] == 1.0 and o[1] == 0.0 and np.isinf(o[2]) and o[3] == np.float32(np.exp(np.float64(-103.0)))
