@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_present_submit", "b200pt_present_acquire",
+    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
     L.b200pt_set_stream.argtypes = [vp, vp]
     L.b200pt_finalize_sum.argtypes = [vp, i32]
     L.b200pt_set_tile_row_range.argtypes = [vp, i32, i32]
+    L.b200pt_set_scene_v4.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.b200pt_present_submit.argtypes = [vp, i32]
     L.b200pt_present_acquire.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(i32)]
     L.b200pt_download_rng_state.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
@@ -171,6 +172,20 @@ class Renderer:
         self._env_keep = e
         t = Texture(_fptr(e), e.shape[1], e.shape[0], 3)
         self._check(self._lib.b200pt_set_env(self._ctx, t), "b200pt_set_env")
+
+    def set_scene_v4(self, quads=None, spheres=None, materials=None, camera_position=(0.0, 0.0, 40.0), camera_distance=1.0):
+        """quads: (nq, 4, 3) vertices; spheres: (ns, 4) xyz+radius; materials: (nq+ns, 17) in SceneMaterial order
+        (albedo3, emissive3, specularChance, specularRoughness, specularColor3, IOR, refractionChance,
+        refractionRoughness, refractionColor3).  No arguments: back to the built-in scene."""
+        q = np.ascontiguousarray(quads if quads is not None else np.zeros((0, 4, 3)), dtype=np.float32).reshape(-1, 12)
+        s = np.ascontiguousarray(spheres if spheres is not None else np.zeros((0, 4)), dtype=np.float32).reshape(-1, 4)
+        m = np.ascontiguousarray(materials if materials is not None else np.zeros((0, 17)), dtype=np.float32).reshape(-1, 17)
+        cam = np.array(list(camera_position) + [camera_distance], dtype=np.float32)
+        if m.shape[0] != q.shape[0] + s.shape[0]:
+            raise ValueError("one material per object")
+        rc = self._lib.b200pt_set_scene_v4(self._ctx, q.ctypes.data_as(ctypes.c_void_p), q.shape[0], s.ctypes.data_as(ctypes.c_void_p),
+                                           s.shape[0], m.ctypes.data_as(ctypes.c_void_p), cam.ctypes.data_as(ctypes.c_void_p))
+        self._check(rc, "b200pt_set_scene_v4")
 
     def resize(self, width, height, ntx, nty):
         self._check(self._lib.b200pt_resize(self._ctx, width, height, ntx, nty), "b200pt_resize")
@@ -281,6 +296,23 @@ def cull_rects(profile, width, height):
     if n.value < 0:
         return None
     return np.array(r[:4 * n.value], dtype=np.float32).reshape(n.value, 4)
+
+
+def cull_rects_scene_v4(quads, spheres, camera_position, camera_distance, width, height):
+    """Host-only: culling rectangles of a run-time OPT_V4 scene, or None when culling is impossible."""
+    L = load_library()
+    vp, i32 = ctypes.c_void_p, ctypes.c_int32
+    L.b200pt_compute_cull_rects_scene_v4.argtypes = [vp, i32, vp, i32, vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
+    q = np.ascontiguousarray(quads, dtype=np.float32).reshape(-1, 12)
+    s = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+    cam = np.array(list(camera_position) + [camera_distance], dtype=np.float32)
+    r = (ctypes.c_float * 48)()
+    n = ctypes.c_int32()
+    rc = L.b200pt_compute_cull_rects_scene_v4(q.ctypes.data_as(vp), q.shape[0], s.ctypes.data_as(vp), s.shape[0],
+                                              cam.ctypes.data_as(vp), width, height, r, ctypes.byref(n))
+    if rc != 0:
+        raise B200PTError("b200pt_compute_cull_rects_scene_v4: invalid argument")
+    return None if n.value < 0 else np.array(r[:4 * n.value], dtype=np.float32).reshape(n.value, 4)
 
 
 def detile(buf, width, height, ntx, nty):

@@ -8,6 +8,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../host/scene_setup.h"
 #include "pt_common.cuh"
@@ -23,6 +24,9 @@ struct b200pt_context {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
 
     SceneSet scenes{};
+    bool custom_scene = false;            // b200pt_set_scene_v4 installed a scene
+    std::vector<float> scene_quads, scene_spheres;  // host copies for the culling rectangles
+    float scene_cam[4] = {0.f, 0.f, 40.f, 1.f};
     float cameraDistance = 1.f;
 
     // target
@@ -93,7 +97,7 @@ LaunchConfig launch_config(const b200pt_context* c)
                      : (c->params.profile == B200PT_PROFILE_OPT_V4 && c->params.env_kind != B200PT_ENV_NONE) ? c->params.env_sampler
                                                                                                               : kSamplerPoint;
     lc.accum_mode = c->params.accum_mode;
-    lc.static_scene = c->params.generic_scene_tables ? 0 : 1;
+    lc.static_scene = (c->params.generic_scene_tables || c->custom_scene) ? 0 : 1;
     lc.block = 256;
     lc.grid = 1;
     return lc;
@@ -313,6 +317,37 @@ int b200pt_set_env(b200pt_context* c, b200pt_texture tex)
     return B200PT_OK;
 }
 
+int b200pt_set_scene_v4(b200pt_context* c, const b200pt_quad* quads, int32_t num_quads, const b200pt_sphere* spheres,
+                        int32_t num_spheres, const b200pt_material* materials, const b200pt_camera* camera)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (c->params.profile != B200PT_PROFILE_OPT_V4) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "runtime scenes exist for the OPT_V4 profile only");
+    CUDA_TRY(c, cudaSetDevice(c->device));
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (num_quads == 0 && num_spheres == 0) {  // back to InitializeScene's scene
+        build_v4_scene(&c->scenes.v4);
+        c->custom_scene = false;
+        return B200PT_OK;
+    }
+    if (!materials || !camera || !(camera->Distance > 0.f))
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "materials and a camera with Distance > 0 are required");
+    static_assert(sizeof(b200pt_quad) == 12 * sizeof(float) && sizeof(b200pt_sphere) == 4 * sizeof(float) &&
+                  sizeof(b200pt_material) == 17 * sizeof(float), "plain float records");
+    V4Scene s;
+    if (!build_v4_scene_from(&s, reinterpret_cast<const float*>(quads), num_quads, reinterpret_cast<const float*>(spheres),
+                             num_spheres, reinterpret_cast<const float*>(materials), camera->Position, camera->Distance))
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "need 1..12 objects (MAX_OBJECTS / MAX_MATERIALS)");
+    c->scenes.v4 = s;
+    c->custom_scene = true;
+    c->scene_quads.assign(reinterpret_cast<const float*>(quads), reinterpret_cast<const float*>(quads) + 12 * (size_t)num_quads);
+    c->scene_spheres.assign(reinterpret_cast<const float*>(spheres), reinterpret_cast<const float*>(spheres) + 4 * (size_t)num_spheres);
+    c->scene_cam[0] = camera->Position[0];
+    c->scene_cam[1] = camera->Position[1];
+    c->scene_cam[2] = camera->Position[2];
+    c->scene_cam[3] = camera->Distance;
+    return B200PT_OK;
+}
+
 int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx, int32_t nty)
 {
     if (!c) return B200PT_ERR_INVALID_ARGUMENT;
@@ -413,7 +448,11 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     rp.nframes = nframes;
     rp.num_bounces = c->params.num_bounces;
     rp.cameraDistance = c->cameraDistance;
-    rp.num_cull_rects = c->params.disable_camera_culling ? -1 : compute_cull_rects(c->params.profile, c->width, c->height, rp.cull_rect);
+    if (c->params.disable_camera_culling) rp.num_cull_rects = -1;
+    else if (c->custom_scene)
+        rp.num_cull_rects = compute_cull_rects_v4(c->scene_quads.data(), c->scenes.v4.numQuads, c->scene_spheres.data(),
+                                                  c->scenes.v4.numSpheres, c->scene_cam, c->scene_cam[3], c->width, c->height, rp.cull_rect);
+    else rp.num_cull_rects = compute_cull_rects(c->params.profile, c->width, c->height, rp.cull_rect);
 
     LaunchConfig lc = launch_config(c);
     // persistent grid: every SM holds blocks_per_sm resident CTAs; warps pull 32-pixel items
@@ -636,6 +675,23 @@ int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float*
         return B200PT_ERR_INVALID_ARGUMENT;
     float4 r[kMaxCullRects];
     const int n = compute_cull_rects(profile, width, height, r);
+    *count = n;
+    for (int i = 0; i < n; i++) {
+        rects[4 * i + 0] = r[i].x; rects[4 * i + 1] = r[i].y; rects[4 * i + 2] = r[i].z; rects[4 * i + 3] = r[i].w;
+    }
+    return B200PT_OK;
+}
+
+int b200pt_compute_cull_rects_scene_v4(const b200pt_quad* quads, int32_t num_quads, const b200pt_sphere* spheres,
+                                       int32_t num_spheres, const b200pt_camera* camera, int32_t width, int32_t height,
+                                       float* rects, int32_t* count)
+{
+    if (!rects || !count || !camera || width <= 0 || height <= 0 || num_quads < 0 || num_spheres < 0 ||
+        num_quads + num_spheres > kV4MaxObjects || (num_quads && !quads) || (num_spheres && !spheres))
+        return B200PT_ERR_INVALID_ARGUMENT;
+    float4 r[kMaxCullRects];
+    const int n = compute_cull_rects_v4(reinterpret_cast<const float*>(quads), num_quads, reinterpret_cast<const float*>(spheres),
+                                        num_spheres, camera->Position, camera->Distance, width, height, r);
     *count = n;
     for (int i = 0; i < n; i++) {
         rects[4 * i + 0] = r[i].x; rects[4 * i + 1] = r[i].y; rects[4 * i + 2] = r[i].z; rects[4 * i + 3] = r[i].w;

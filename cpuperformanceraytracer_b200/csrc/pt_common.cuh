@@ -53,13 +53,17 @@ struct V4Material {
     v3 albedo, emissive, specularColor, refractionColor;
     float specularChance, specularRoughness, IOR, refractionChance, refractionRoughness;
 };
-constexpr int kV4Quads = 4;
+constexpr int kV4Quads = 4;    // the built-in scene of InitializeScene
 constexpr int kV4Spheres = 7;
 constexpr int kV4Objects = kV4Quads + kV4Spheres;
+constexpr int kV4MaxObjects = 12;  // MAX_OBJECTS / MAX_MATERIALS, v4.cpp:327-328: one material per object
+// `struct Scene` (v4.cpp:364-378) + `struct Camera` (:380-386) as data: the built-in scene, or whatever
+// b200pt_set_scene_v4 installed.  Object (= material) index: quads first, then spheres (v4.cpp:702-715).
 struct V4Scene {
-    V4Quad quad[kV4Quads];
-    float4 sphere[kV4Spheres];
-    V4Material mat[kV4Objects];
+    int numQuads, numSpheres;
+    V4Quad quad[kV4MaxObjects];
+    float4 sphere[kV4MaxObjects];
+    V4Material mat[kV4MaxObjects];
     v3 cameraPosition;
     float cameraDistance;
 };

@@ -94,6 +94,8 @@ static void precompute_quad(V4Quad* q, v3 V0, v3 V1, v3 V2, v3 V3)
 void build_v4_scene(V4Scene* s)
 {
     std::memset(s, 0, sizeof(*s));
+    s->numQuads = kV4Quads;
+    s->numSpheres = kV4Spheres;
     const v3 T = mk(0.0f, 0.0f, 10.0f);  // v4.cpp:1407
     precompute_quad(&s->quad[0], add(mk(-25.0f, -12.5f, 5.0f), T), add(mk(25.0f, -12.5f, 5.0f), T),
                     add(mk(25.0f, -12.5f, -5.0f), T), add(mk(-25.0f, -12.5f, -5.0f), T));           // floor :1416-1419
@@ -125,6 +127,36 @@ void build_v4_scene(V4Scene* s)
     }
     s->cameraDistance = camera_distance();
     s->cameraPosition = mk(0.f, 0.f, 1.f * 40.f);  // v4.cpp:1501
+}
+
+bool build_v4_scene_from(V4Scene* s, const float* qv, int nq, const float* sp, int ns, const float* mats,
+                         const float cam_pos[3], float cam_dist)
+{
+    if (nq < 0 || ns < 0 || nq + ns < 1 || nq + ns > kV4MaxObjects || (nq && !qv) || (ns && !sp) || !mats || !cam_pos) return false;
+    std::memset(s, 0, sizeof(*s));
+    s->numQuads = nq;
+    s->numSpheres = ns;
+    for (int i = 0; i < nq; i++) {
+        const float* v = qv + 12 * i;
+        precompute_quad(&s->quad[i], mk(v[0], v[1], v[2]), mk(v[3], v[4], v[5]), mk(v[6], v[7], v[8]), mk(v[9], v[10], v[11]));
+    }
+    for (int i = 0; i < ns; i++) s->sphere[i] = make_float4(sp[4 * i], sp[4 * i + 1], sp[4 * i + 2], sp[4 * i + 3]);
+    for (int i = 0; i < nq + ns; i++) {
+        const float* m = mats + 17 * i;
+        V4Material& d = s->mat[i];
+        d.albedo = mk(m[0], m[0], m[0]);  // AddMaterialToScene stores albedo.x three times, v4.cpp:1370-1372
+        d.emissive = mk(m[3], m[4], m[5]);
+        d.specularChance = m[6];
+        d.specularRoughness = m[7];
+        d.specularColor = mk(m[8], m[9], m[10]);
+        d.IOR = m[11];
+        d.refractionChance = m[12];
+        d.refractionRoughness = m[13];
+        d.refractionColor = mk(m[14], m[15], m[16]);
+    }
+    s->cameraPosition = mk(cam_pos[0], cam_pos[1], cam_pos[2]);
+    s->cameraDistance = cam_dist;
+    return true;
 }
 
 // Scene of demofox_path_tracing_v3_redo.cpp, SCENE 1 (:485-600)
@@ -173,17 +205,18 @@ void build_v3redo_scene(V3RedoScene* s)
 namespace {
 struct Box { double lo[3], hi[3]; };
 
-bool project_box(const Box& b, int profile, int W, int H, double camDist, float4* out)
+bool project_box(const Box& b, int profile, int W, int H, double camDist, float4* out, const double* camPos = nullptr)
 {
+    const double cx = camPos ? camPos[0] : 0.0, cy = camPos ? camPos[1] : 0.0, cz = camPos ? camPos[2] : 40.0;
     double x0 = 1e300, y0 = 1e300, x1 = -1e300, y1 = -1e300;
     for (int k = 0; k < 8; k++) {
         const double px = (k & 1) ? b.hi[0] : b.lo[0], py = (k & 2) ? b.hi[1] : b.lo[1], pz = (k & 4) ? b.hi[2] : b.lo[2];
         double tx, ty;
         if (profile == kProfileV4) {
-            const double depth = (40.0 - pz) / camDist;  // camera at (0, 0, 40) looking down -z
+            const double depth = (cz - pz) / camDist;  // camera (default (0, 0, 40)) looking down -z
             if (depth < 1e-3) return false;
-            tx = px / depth;
-            ty = py / depth * ((double)W / (double)H);
+            tx = (px - cx) / depth;
+            ty = (py - cy) / depth * ((double)W / (double)H);
         } else {
             const double depth = pz / camDist;  // camera at the origin looking down +z
             if (depth < 1e-3) return false;
@@ -221,6 +254,29 @@ Box sphere_box(const float4& s)
     return b;
 }
 }  // namespace
+
+int compute_cull_rects_v4(const float* qv, int nq, const float* sp, int ns, const float cam_pos[3], float cam_dist, int width,
+                          int height, float4* rects)
+{
+    if (nq + ns > kMaxCullRects || !(cam_dist > 0.f)) return -1;
+    const double cp[3] = {cam_pos[0], cam_pos[1], cam_pos[2]};
+    int n = 0;
+    for (int i = 0; i < nq; i++) {
+        Box b = empty_box();
+        for (int k = 0; k < 4; k++) grow(&b, mk(qv[12 * i + 3 * k], qv[12 * i + 3 * k + 1], qv[12 * i + 3 * k + 2]));
+        for (int a = 0; a < 3; a++) {
+            const double pad = 1e-3 + 1e-5 * (std::fabs(b.lo[a]) + std::fabs(b.hi[a]));
+            b.lo[a] -= pad;
+            b.hi[a] += pad;
+        }
+        if (!project_box(b, kProfileV4, width, height, cam_dist, &rects[n++], cp)) return -1;
+    }
+    for (int i = 0; i < ns; i++)
+        if (!project_box(sphere_box(make_float4(sp[4 * i], sp[4 * i + 1], sp[4 * i + 2], std::fabs(sp[4 * i + 3]))), kProfileV4, width,
+                         height, cam_dist, &rects[n++], cp))
+            return -1;
+    return n;
+}
 
 int compute_cull_rects(int profile, int width, int height, float4* rects)
 {

@@ -7,6 +7,14 @@ float camera_distance();
 void build_cornell_scene(CornellScene* s, bool simt_textured_materials);
 void build_v4_scene(V4Scene* s);
 void build_v3redo_scene(V3RedoScene* s);
+// AddQuadObjectToScene / AddSphereObjectToScene / AddMaterialToScene (v4.cpp:1368-1401) on caller data:
+// quads as 4 vertices (12 floats each), spheres as xyz + radius, materials in the 17-float order of
+// SceneMaterial (v4.cpp:351-362); like AddMaterialToScene, albedo.y / albedo.z are replaced by albedo.x.
+bool build_v4_scene_from(V4Scene* s, const float* quad_vertices, int num_quads, const float* spheres, int num_spheres,
+                         const float* materials, const float camera_position[3], float camera_distance);
+// culling rectangles for an arbitrary v4-profile scene (quad vertices / spheres as above)
+int compute_cull_rects_v4(const float* quad_vertices, int num_quads, const float* spheres, int num_spheres,
+                          const float camera_position[3], float camera_distance, int width, int height, float4* rects);
 // Conservative fragCoord-space rectangles (x0, y0, x1, y1) that contain the projection of every
 // primitive of the profile's scene, expanded by a safety margin.  Returns the number of rectangles,
 // or -1 when culling is not possible (a primitive reaches behind the camera).

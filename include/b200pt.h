@@ -116,6 +116,26 @@ int b200pt_default_params(int profile, b200pt_params* p);
 int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx);
 int b200pt_destroy(b200pt_context* ctx);
 
+/* Runtime scene description for B200PT_PROFILE_OPT_V4: the data the reference
+ * hard-codes in InitializeScene / InitializeCamera (..._optimization_v4.cpp:1403-1502), installed
+ * through the equivalents of AddQuadObjectToScene / AddSphereObjectToScene / AddMaterialToScene
+ * (:1368-1401).  Object i owns material i; quads come first, then spheres; at most 12 objects
+ * (MAX_OBJECTS / MAX_MATERIALS, :327-328).  Quad data is precomputed exactly like PrecomputeQuadData
+ * (:269-319).  Like AddMaterialToScene, albedo[1] and albedo[2] are ignored (albedo[0] is stored in all
+ * three channels, :1370-1372).  Pass num_quads = num_spheres = 0 to return to the built-in scene. */
+typedef struct b200pt_quad { float V0[3], V1[3], V2[3], V3[3]; } b200pt_quad;          /* QuadSceneObject, :248-255 */
+typedef struct b200pt_sphere { float PositionAndRadius[4]; } b200pt_sphere;               /* SphereSceneObject, :321-324 */
+typedef struct b200pt_material {                                                         /* SceneMaterial, :351-362 */
+    float albedo[3], emissive[3];
+    float specularChance, specularRoughness;
+    float specularColor[3];
+    float IOR, refractionChance, refractionRoughness;
+    float refractionColor[3];
+} b200pt_material;
+typedef struct b200pt_camera { float Position[3]; float Distance; } b200pt_camera;       /* Camera, :380-386 */
+int b200pt_set_scene_v4(b200pt_context* ctx, const b200pt_quad* quads, int32_t num_quads, const b200pt_sphere* spheres,
+                        int32_t num_spheres, const b200pt_material* materials, const b200pt_camera* camera);
+
 /* Uploads the environment texture once (the reference re-passes `texture Texture` by value on
  * every render call, ..._optimization_v4.cpp:1696-1699).  Cubemaps are the W x 6H atlas that
  * LoadCubemapTexture builds (asset_loading.cpp:18-44). */
@@ -191,6 +211,10 @@ int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
  * y = flipped row index) outside of which a camera ray of `profile` cannot hit the scene; the kernel
  * skips the scene trace for such pixels.  rects must hold 4 * 12 floats; *count < 0 = no culling. */
 int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float* rects, int32_t* count);
+/* same for a run-time OPT_V4 scene (see b200pt_set_scene_v4) */
+int b200pt_compute_cull_rects_scene_v4(const b200pt_quad* quads, int32_t num_quads, const b200pt_sphere* spheres,
+                                       int32_t num_spheres, const b200pt_camera* camera, int32_t width, int32_t height,
+                                       float* rects, int32_t* count);
 
 int b200pt_get_counters(b200pt_context* ctx, b200pt_counters* out);
 const char* b200pt_last_error(b200pt_context* ctx);

@@ -378,11 +378,13 @@ typedef struct {
     v3 albedo, emissive, specularColor, refractionColor;
     float specularChance, specularRoughness, IOR, refractionChance, refractionRoughness;
 } mat4_t;
+#define MAX_OBJECTS 12 /* v4.cpp:327-328 */
 typedef struct {
-    quad4_t quad[4];
-    v3 sphereCenter[7];
-    float sphereRadius[7];
-    mat4_t mat[11];
+    int numQuads, numSpheres;
+    quad4_t quad[MAX_OBJECTS];
+    v3 sphereCenter[MAX_OBJECTS];
+    float sphereRadius[MAX_OBJECTS];
+    mat4_t mat[MAX_OBJECTS];
     v3 cameraPosition;
     float cameraDistance;
 } scene4_t;
@@ -411,6 +413,8 @@ static void scene4_init(scene4_t* s)
 {
     const v3 T = V3(0.0f, 0.0f, 10.0f);
     memset(s, 0, sizeof(*s));
+    s->numQuads = 4;
+    s->numSpheres = 7;
     quad4_init(&s->quad[0], add3(V3(-25.0f, -12.5f, 5.0f), T), add3(V3(25.0f, -12.5f, 5.0f), T),
                add3(V3(25.0f, -12.5f, -5.0f), T), add3(V3(-25.0f, -12.5f, -5.0f), T));
     quad4_init(&s->quad[1], V3(-25.0f, -1.5f, 5.0f), V3(25.0f, -1.5f, 5.0f), V3(25.0f, -10.5f, 5.0f),
@@ -440,6 +444,40 @@ static void scene4_init(scene4_t* s)
     }
     s->cameraDistance = oracle_camera_distance();
     s->cameraPosition = V3(0.f, 0.f, 1.f * 40.f); /* v4.cpp:1501 */
+}
+
+/* AddQuadObjectToScene / AddSphereObjectToScene / AddMaterialToScene (v4.cpp:1368-1401) on caller data */
+static int scene4_from(scene4_t* s, const oracle_scene_v4* src)
+{
+    int nq = src->num_quads, ns = src->num_spheres;
+    if (nq < 0 || ns < 0 || nq + ns < 1 || nq + ns > MAX_OBJECTS || !src->materials) return -1;
+    memset(s, 0, sizeof(*s));
+    s->numQuads = nq;
+    s->numSpheres = ns;
+    for (int i = 0; i < nq; i++) {
+        const float* v = src->quad_vertices + 12 * i;
+        quad4_init(&s->quad[i], V3(v[0], v[1], v[2]), V3(v[3], v[4], v[5]), V3(v[6], v[7], v[8]), V3(v[9], v[10], v[11]));
+    }
+    for (int i = 0; i < ns; i++) {
+        s->sphereCenter[i] = V3(src->spheres[4 * i], src->spheres[4 * i + 1], src->spheres[4 * i + 2]);
+        s->sphereRadius[i] = src->spheres[4 * i + 3];
+    }
+    for (int i = 0; i < nq + ns; i++) {
+        const float* m = src->materials + 17 * i;
+        mat4_t* d = &s->mat[i];
+        d->albedo = V3(m[0], m[0], m[0]); /* albedo.x three times, v4.cpp:1370-1372 */
+        d->emissive = V3(m[3], m[4], m[5]);
+        d->specularChance = m[6];
+        d->specularRoughness = m[7];
+        d->specularColor = V3(m[8], m[9], m[10]);
+        d->IOR = m[11];
+        d->refractionChance = m[12];
+        d->refractionRoughness = m[13];
+        d->refractionColor = V3(m[14], m[15], m[16]);
+    }
+    s->cameraPosition = V3(src->camera_position[0], src->camera_position[1], src->camera_position[2]);
+    s->cameraDistance = src->camera_distance;
+    return 0;
 }
 
 /* v4.cpp:575-645 */
@@ -643,10 +681,10 @@ static v3 GetColorForRay_v4(const ctx_t* c, v3 rayPos, v3 rayDir, uint32_t* rng,
         hit_t h;
         h.fromInside = 0; h.dist = c_superFar; h.normal = V3(0.f, 0.f, 0.f); h.matIndex = 0;
         st->segments++;
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < s->numQuads; i++)
             if (TestQuadTrace_v4(rayPos, rayDir, &h, &s->quad[i])) h.matIndex = i;
-        for (int i = 0; i < 7; i++)
-            if (TestSphereTrace_v4(rayPos, rayDir, &h, s->sphereCenter[i], s->sphereRadius[i])) h.matIndex = 4 + i;
+        for (int i = 0; i < s->numSpheres; i++)
+            if (TestSphereTrace_v4(rayPos, rayDir, &h, s->sphereCenter[i], s->sphereRadius[i])) h.matIndex = s->numQuads + i;
         int miss = (h.dist == c_superFar);
         /* the env lookup runs for every lane on every segment (and draws 2 numbers in
          * random-jitter mode); only a missing lane uses the value, :753-778 */
@@ -888,6 +926,7 @@ static int ctx_init(ctx_t* c, const oracle_params* p)
     c->p = p;
     cornell_init(&c->cornell, p->profile);
     scene4_init(&c->scene4);
+    if (p->profile == ORACLE_PROFILE_V4 && p->scene_v4 && scene4_from(&c->scene4, p->scene_v4)) return -1;
     scene3_init(&c->scene3);
     c->tex.data = p->env; c->tex.W = p->env_width; c->tex.H = p->env_height;
     return 0;

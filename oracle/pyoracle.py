@@ -20,6 +20,12 @@ ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
 SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
 
 
+class OracleSceneV4(ctypes.Structure):
+    _fields_ = [("num_quads", ctypes.c_int), ("num_spheres", ctypes.c_int), ("quad_vertices", ctypes.POINTER(ctypes.c_float)),
+                ("spheres", ctypes.POINTER(ctypes.c_float)), ("materials", ctypes.POINTER(ctypes.c_float)),
+                ("camera_position", ctypes.c_float * 3), ("camera_distance", ctypes.c_float)]
+
+
 class OracleParams(ctypes.Structure):
     _fields_ = [
         ("profile", ctypes.c_int),
@@ -33,6 +39,7 @@ class OracleParams(ctypes.Structure):
         ("env", ctypes.POINTER(ctypes.c_float)),
         ("env_width", ctypes.c_int),
         ("env_height", ctypes.c_int),
+        ("scene_v4", ctypes.POINTER(OracleSceneV4)),
     ]
 
 
@@ -75,6 +82,20 @@ def lib():
     return _lib
 
 
+def make_scene_v4(quads, spheres, materials, camera_position=(0.0, 0.0, 40.0), camera_distance=1.0):
+    """Returns (OracleSceneV4, keepalive) from (nq,4,3) / (ns,4) / (nq+ns,17) arrays."""
+    q = np.ascontiguousarray(quads, dtype=np.float32).reshape(-1, 12)
+    s = np.ascontiguousarray(spheres, dtype=np.float32).reshape(-1, 4)
+    m = np.ascontiguousarray(materials, dtype=np.float32).reshape(-1, 17)
+    sc = OracleSceneV4()
+    sc.num_quads, sc.num_spheres = q.shape[0], s.shape[0]
+    fp = ctypes.POINTER(ctypes.c_float)
+    sc.quad_vertices, sc.spheres, sc.materials = q.ctypes.data_as(fp), s.ctypes.data_as(fp), m.ctypes.data_as(fp)
+    sc.camera_position = (ctypes.c_float * 3)(*camera_position)
+    sc.camera_distance = camera_distance
+    return sc, (q, s, m)
+
+
 def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=ENV_NONE, env_sampler=SAMPLER_POINT):
     p = OracleParams()
     p.profile, p.width, p.height = profile, width, height
@@ -90,9 +111,11 @@ def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=EN
 
 
 def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, env=None, env_kind=ENV_NONE,
-           env_sampler=SAMPLER_POINT, target=None, nthreads=0):
-    """Returns (tile-major f32 buffer, counters dict)."""
+           env_sampler=SAMPLER_POINT, target=None, nthreads=0, scene_v4=None):
+    """Returns (tile-major f32 buffer, counters dict).  scene_v4: result of make_scene_v4 (V4 profile)."""
     p, keep = make_params(profile, width, height, ntx, nty, bounces, env, env_kind, env_sampler)
+    if scene_v4 is not None:
+        p.scene_v4 = ctypes.pointer(scene_v4[0])
     if target is None:
         target = np.zeros(width * height * 3, dtype=np.float32)
     else:
@@ -107,9 +130,11 @@ def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, en
 
 
 def max_segments(profile, width, height, bounces, nframes, first_frame=1, env=None, env_kind=ENV_NONE,
-                 env_sampler=SAMPLER_POINT):
+                 env_sampler=SAMPLER_POINT, scene_v4=None):
     """(H, W) uint32: max traced segments per pixel over the frame range."""
     p, keep = make_params(profile, width, height, 1, 1, bounces, env, env_kind, env_sampler)
+    if scene_v4 is not None:
+        p.scene_v4 = ctypes.pointer(scene_v4[0])
     out = np.zeros(width * height, dtype=np.uint32)
     L = lib()
     L.oracle_max_segments.argtypes = [ctypes.POINTER(OracleParams), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)]
