@@ -45,6 +45,25 @@ F_ACC = 9                           # per path: running-average blend (3 x sub, 
 ACC_BYTES_PER_PIXEL_PER_LAUNCH = 24  # f32 target read + write once per launch
 
 
+def measured_dram_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of pt_render_kernel from the newest committed ncu capture
+    (profiles/*_metrics.csv, written by scripts/ncu_summary.py from an `ncu --set full` report); bytes per launch."""
+    import csv
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_parity_v2_*_metrics.csv"))):
+        best = path
+    if not best:
+        return None, None
+    unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    tot = 0.0
+    with open(best) as f:
+        for row in csv.reader(f):
+            if len(row) == 3 and row[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+                tot += float(row[2]) * unit.get(row[1], 1.0)
+    return (tot if tot > 0 else None), os.path.relpath(best, ROOT)
+
+
 def load_peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -309,10 +328,11 @@ def main():
         fp32_peak = 148 * 128 * 2 * peaks["sm_max_mhz"] * 1e6 * 1e-12 * world  # TFLOP/s, FFMA = 2 flop
         achieved = flops_per_step / (step_ms * 1e-3) * 1e-12
         hbm_bytes = WIDTH * HEIGHT * ACC_BYTES_PER_PIXEL_PER_LAUNCH * world
+        traffic, traffic_src = measured_dram_traffic()
         roofline = {
             "bound": "fp32",
             "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-            "traffic": None,
+            "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {peaks['sm_max_mhz']:.0f} MHz "
                            f"(MEASURED_PEAKS.json clock, {peaks['source']}); the file's hbm/bf16 peaks do not bound this kernel",
             "algorithmic_flops_per_segment": F_SEG_V2, "segments_per_path": segs / total_paths,
