@@ -65,6 +65,23 @@ struct b200pt_context {
 
 namespace {
 
+// Every entry point works on the context's device but leaves the caller's current device untouched
+// (a host application -- or torch in the multi-GPU driver -- owns that setting).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t status = cudaSuccess;
+    explicit DeviceGuard(int device)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        status = (prev == device) ? cudaSuccess : cudaSetDevice(device);
+    }
+    ~DeviceGuard()
+    {
+        int cur = -1;
+        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
+    }
+};
+
 int fail(b200pt_context* ctx, int code, const std::string& msg)
 {
     if (ctx) ctx->last_error = msg;
@@ -219,8 +236,9 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
         delete c;
         return B200PT_ERR_CUDA;  // no CPU fallback
     }
+    DeviceGuard guard(c->device);
     cudaDeviceProp prop{};
-    if (cudaSetDevice(c->device) != cudaSuccess || cudaGetDeviceProperties(&prop, c->device) != cudaSuccess ||
+    if (guard.status != cudaSuccess || cudaGetDeviceProperties(&prop, c->device) != cudaSuccess ||
         prop.major < 10) {
         delete c;
         return B200PT_ERR_CUDA;  // kernels are sm_100a only
@@ -262,7 +280,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
 int b200pt_destroy(b200pt_context* c)
 {
     if (!c) return B200PT_ERR_INVALID_ARGUMENT;
-    cudaSetDevice(c->device);
+    DeviceGuard guard(c->device);
     if (c->own_stream) cudaStreamSynchronize(c->own_stream);
     free_target(c);
     free_env(c);
@@ -288,7 +306,8 @@ int b200pt_set_env(b200pt_context* c, b200pt_texture tex)
     // the reference indexes texels through binary32 arithmetic (texture.cpp:56-65,84): exact up to 2^24 floats
     if ((long long)tex.Width * tex.Height * 3 >= (1LL << 24))
         return fail(c, B200PT_ERR_INVALID_ARGUMENT, "env texture too large for the reference's float texel indexing");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     const size_t texels = (size_t)tex.Width * tex.Height;
     if (texels != (size_t)c->env_w * c->env_h) {
@@ -322,7 +341,8 @@ int b200pt_set_scene_v4(b200pt_context* c, const b200pt_quad* quads, int32_t num
 {
     if (!c) return B200PT_ERR_INVALID_ARGUMENT;
     if (c->params.profile != B200PT_PROFILE_OPT_V4) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "runtime scenes exist for the OPT_V4 profile only");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (num_quads == 0 && num_spheres == 0) {  // back to InitializeScene's scene
         build_v4_scene(&c->scenes.v4);
@@ -355,7 +375,8 @@ int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx,
     if (width <= 0 || height <= 0 || ntx <= 0 || nty <= 0 || width % ntx || height % nty || (width / ntx) % 8)
         return fail(c, B200PT_ERR_INVALID_ARGUMENT, "invalid tiling: need W % ntx == 0, H % nty == 0, tile width % 8 == 0");
     if ((long long)width * height * 3 >= (1LL << 31)) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "image too large");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     const size_t nfloats = (size_t)width * height * 3;
     const bool bound = c->d_target && c->d_target != c->d_target_own;
@@ -382,7 +403,8 @@ int b200pt_reset(b200pt_context* c)
 {
     if (!c) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     const size_t nfloats = (size_t)c->width * c->height * 3;
     CUDA_TRY(c, cudaMemsetAsync(c->d_target, 0, nfloats * sizeof(float), c->stream));  // Application.cpp:151
     CUDA_TRY(c, cudaMemsetAsync(c->d_screen, 0, (size_t)c->width * c->height * 4, c->stream));
@@ -419,7 +441,8 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
     if (uses_env(c->params) && !c->env_tex) return fail(c, B200PT_ERR_NOT_READY, "this profile samples an env map: set_env first");
     if (nframes == 0) return B200PT_OK;
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
 
     RenderParams rp{};
@@ -448,6 +471,13 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     rp.nframes = nframes;
     rp.num_bounces = c->params.num_bounces;
     rp.cameraDistance = c->cameraDistance;
+    rp.rcp_width = 1.0f / (float)c->width;
+    rp.rcp_height = 1.0f / (float)c->height;
+    {
+        // significant bits of an integer = bit length minus trailing zeros
+        auto sig_bits = [](unsigned v) { int len = 0, tz = 0; for (unsigned t = v; t; t >>= 1) len++; while (v && !(v & 1u)) { v >>= 1; tz++; } return len - tz; };
+        rp.res_div_exact = (sig_bits((unsigned)c->width) <= 16 && sig_bits((unsigned)c->height) <= 16) ? 1 : 0;
+    }
     if (c->params.disable_camera_culling) rp.num_cull_rects = -1;
     else if (c->custom_scene)
         rp.num_cull_rects = compute_cull_rects_v4(c->scene_quads.data(), c->scenes.v4.numQuads, c->scene_spheres.data(),
@@ -480,7 +510,8 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
 int b200pt_synchronize(b200pt_context* c)
 {
     if (!c) return B200PT_ERR_INVALID_ARGUMENT;
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     return collect_timing(c);
 }
@@ -489,7 +520,8 @@ int b200pt_upload_target(b200pt_context* c, const float* host_src)
 {
     if (!c || !host_src) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaMemcpyAsync(c->d_target, host_src, (size_t)c->width * c->height * 3 * sizeof(float),
                                 cudaMemcpyHostToDevice, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -500,7 +532,8 @@ int b200pt_download_target(b200pt_context* c, float* host_dst)
 {
     if (!c || !host_dst) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_target, (size_t)c->width * c->height * 3 * sizeof(float),
                                 cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -515,7 +548,8 @@ int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H
     if (NumChannels != 3) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "NumChannels must be 3");
     if (NumTilesX <= 0 || NumTilesY <= 0 || TileWidth * NumTilesX != W || TileHeight * NumTilesY != H)
         return fail(c, B200PT_ERR_INVALID_ARGUMENT, "tiles must cover the buffer exactly");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     if (c->width != W || c->height != H || c->ntx != NumTilesX || c->nty != NumTilesY) {
         const int keep_frame = c->iframe;
         int rc = b200pt_resize(c, W, H, NumTilesX, NumTilesY);
@@ -558,7 +592,8 @@ int b200pt_resolve_ldr(b200pt_context* c, uint32_t* host_dst, int32_t mode, int3
 {
     if (!c || !host_dst || (mode != B200PT_LDR_FILE_RGBA && mode != B200PT_LDR_SCREEN_BGRA)) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));  // the present ring may still be reading slot 0
     CUDA_TRY(c, launch_resolve_ldr(c->d_target, c->d_screen, c->width, c->height, c->tile_w, c->tile_h, c->ntx, mode, c->stream));
     c->launches++;
@@ -578,7 +613,8 @@ int b200pt_present_submit(b200pt_context* c, int32_t nframes)
     if (!c || nframes <= 0) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
     if (c->submitted - c->acquired >= 2) return fail(c, B200PT_ERR_NOT_READY, "present ring full: acquire a frame first");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     const size_t bytes = (size_t)c->width * c->height * sizeof(uint32_t);
     if (!c->d_screen1) CUDA_TRY(c, cudaMalloc(&c->d_screen1, bytes));
     for (int i = 0; i < 2; i++)
@@ -600,7 +636,8 @@ int b200pt_present_acquire(b200pt_context* c, const uint32_t** frame, int32_t* i
 {
     if (!c || !frame) return B200PT_ERR_INVALID_ARGUMENT;
     if (c->acquired >= c->submitted) return fail(c, B200PT_ERR_NOT_READY, "no frame in flight");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     const int slot = (int)(c->acquired & 1ull);
     CUDA_TRY(c, cudaEventSynchronize(c->copy_done[slot]));
     *frame = c->h_ring[slot];
@@ -629,7 +666,8 @@ int b200pt_get_device_target(b200pt_context* c, void** device_ptr, size_t* bytes
 int b200pt_set_stream(b200pt_context* c, void* cuda_stream)
 {
     if (!c) return B200PT_ERR_INVALID_ARGUMENT;
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
@@ -651,7 +689,8 @@ int b200pt_finalize_sum(b200pt_context* c, int32_t total_frames)
 {
     if (!c || total_frames < 0) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     const float scale = 1.0f / ((float)total_frames + 1.f);
     CUDA_TRY(c, launch_scale(c->d_target, (size_t)c->width * c->height * 3, scale, c->stream));
     c->launches++;
@@ -662,7 +701,8 @@ int b200pt_download_rng_state(b200pt_context* c, uint32_t* host_dst)
 {
     if (!c || !host_dst) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_rng) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_rng, (size_t)c->width * c->height * sizeof(uint32_t), cudaMemcpyDeviceToHost,
                                 c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
@@ -702,7 +742,8 @@ int b200pt_compute_cull_rects_scene_v4(const b200pt_quad* quads, int32_t num_qua
 int b200pt_get_counters(b200pt_context* c, b200pt_counters* out)
 {
     if (!c || !out) return B200PT_ERR_INVALID_ARGUMENT;
-    CUDA_TRY(c, cudaSetDevice(c->device));
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
     DeviceCounters dc{};

@@ -117,6 +117,8 @@ struct RenderParams {
     int nframes;
     int num_bounces;
     float cameraDistance;     // 1 / tan(FOV/2), computed on the host like v2.cpp:546
+    float rcp_width, rcp_height;  // RN(1/W), RN(1/H), host-computed
+    int res_div_exact;        // W and H have <= 16 significant bits: x / W == fma(fma(-q, W, x), rcp, q), q = x * rcp
     // conservative screen-space bounds of the scene's primitives in fragCoord space
     // (x0, y0, x1, y1; y = flipped row): a pixel whose jitter footprint overlaps none of them cannot
     // hit anything, so its paths skip the scene trace (host/scene_setup.cpp: compute_cull_rects)
