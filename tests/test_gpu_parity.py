@@ -281,3 +281,17 @@ def test_present_ring_frames_are_the_reference_screen_frames(oracle):
                                target=buf)
         assert iframe == k
         assert np.array_equal(img, oracle.resolve_ldr(buf, W, H, ntx, nty, mode=1)), k
+
+
+def test_full_size_bit_exact_vs_oracle(oracle):
+    """BASELINE config 2 geometry (1920x1080, tiles 10x15, 8 bounces) at a bounded spp: the whole f32
+    buffer, the RNG states and the counters equal the oracle's, bit for bit (the oracle takes ~10 s)."""
+    W, H, ntx, nty, frames = 1920, 1080, 10, 15, 6
+    o, oc = oracle.render(oracle.PROFILE_V2, W, H, ntx, nty, 8, frames)
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=8) as r:
+        r.resize(W, H, ntx, nty)
+        r.render_frames(frames)
+        g = r.download_target()
+        c = r.counters()
+    assert np.array_equal(g, o)
+    assert (c["paths"], c["segments"], c["escapes"]) == (oc["paths"], oc["segments"], oc["escapes"])
