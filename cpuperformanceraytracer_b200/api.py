@@ -27,7 +27,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
+    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
 ]
 
 
@@ -91,6 +91,7 @@ def load_library():
     L.b200pt_set_stream.argtypes = [vp, vp]
     L.b200pt_finalize_sum.argtypes = [vp, i32]
     L.b200pt_set_tile_row_range.argtypes = [vp, i32, i32]
+    L.b200pt_set_tile_range.argtypes = [vp, i32, i32]
     L.b200pt_set_scene_v4.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.b200pt_present_submit.argtypes = [vp, i32]
     L.b200pt_present_acquire.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(i32)]
@@ -281,6 +282,9 @@ class Renderer:
     def set_tile_row_range(self, first_tile_row, num_tile_rows):
         self._check(self._lib.b200pt_set_tile_row_range(self._ctx, int(first_tile_row), int(num_tile_rows)),
                     "b200pt_set_tile_row_range")
+
+    def set_tile_range(self, first_flat_tile, num_tiles):
+        self._check(self._lib.b200pt_set_tile_range(self._ctx, int(first_flat_tile), int(num_tiles)), "b200pt_set_tile_range")
 
     def finalize_sum(self, total_frames):
         self._check(self._lib.b200pt_finalize_sum(self._ctx, int(total_frames)), "b200pt_finalize_sum")

@@ -91,7 +91,7 @@ def build_host(force=False):
     srcs = [os.path.join(HOST, f) for f in ("demofox_render.cpp", "image_io.cpp")]
     if not all(os.path.exists(s) for s in srcs):
         return
-    hdrs = [os.path.join(HOST, f) for f in ("demofox_render.h", "image_io.h", "global_preprocessor_flags.h")]
+    hdrs = [os.path.join(HOST, f) for f in ("demofox_render.h", "image_io.h", "global_preprocessor_flags.h", "tiles.h")]
     flags = ["-std=c++17", "-O2", "-fPIC", "-ffp-contract=off", "-I", os.path.join(ROOT, "include"), "-I", HOST]
     rpath = ["-Wl,-rpath,$ORIGIN"]
     if force or _stale(HOSTLIB, srcs + hdrs + [LIB]):

@@ -55,7 +55,7 @@ struct b200pt_context {
     const float* last_env_ptr = nullptr;
 
     int iframe = 0;
-    int first_tile_row = 0, num_tile_rows = 0;  // band rendered by this context (0, 0 = all rows)
+    int first_tile = 0, num_tiles = 0;  // flat tile range rendered by this context (0, 0 = all tiles)
     int blocks_per_sm = 0;
     uint64_t paths = 0, launches = 0;
     double last_render_ms = 0.0;
@@ -395,7 +395,7 @@ int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx,
     c->nty = nty;
     c->tile_w = width / ntx;
     c->tile_h = height / nty;
-    c->first_tile_row = c->num_tile_rows = 0;
+    c->first_tile = c->num_tiles = 0;
     return b200pt_reset(c);
 }
 
@@ -462,10 +462,10 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     rp.num_tiles_x = c->ntx;
     rp.groups_per_tile_row = c->tile_w / 8;
     rp.groups_per_tile = rp.groups_per_tile_row * c->tile_h;
-    const int groups_per_tile_band = rp.groups_per_tile * c->ntx;  // one row of tiles is contiguous in memory
-    const int band_rows = c->num_tile_rows > 0 ? c->num_tile_rows : c->nty;
-    rp.group_offset = (c->num_tile_rows > 0 ? c->first_tile_row : 0) * groups_per_tile_band;
-    rp.num_groups = band_rows * groups_per_tile_band;
+    // tiles follow one another in FlatTileIndex order in the buffer (RenderTile, v4.cpp:1189-1194)
+    const int ntiles = c->num_tiles > 0 ? c->num_tiles : c->ntx * c->nty;
+    rp.group_offset = (c->num_tiles > 0 ? c->first_tile : 0) * rp.groups_per_tile;
+    rp.num_groups = ntiles * rp.groups_per_tile;
     rp.num_items = (rp.num_groups + 3) / 4;
     rp.first_frame = c->iframe + 1;  // iFrame += 1 before the render, v4.cpp:1703
     rp.nframes = nframes;
@@ -680,8 +680,19 @@ int b200pt_set_tile_row_range(b200pt_context* c, int32_t first_tile_row, int32_t
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
     if (first_tile_row < 0 || num_tile_rows < 0 || first_tile_row + num_tile_rows > c->nty)
         return fail(c, B200PT_ERR_INVALID_ARGUMENT, "tile row range outside the image");
-    c->first_tile_row = first_tile_row;
-    c->num_tile_rows = num_tile_rows;
+    c->first_tile = first_tile_row * c->ntx;
+    c->num_tiles = num_tile_rows * c->ntx;
+    return B200PT_OK;
+}
+
+int b200pt_set_tile_range(b200pt_context* c, int32_t first_flat_tile, int32_t num_tiles)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    if (first_flat_tile < 0 || num_tiles < 0 || first_flat_tile + num_tiles > c->ntx * c->nty)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "tile range outside the image");
+    c->first_tile = first_flat_tile;
+    c->num_tiles = num_tiles;
     return B200PT_OK;
 }
 

@@ -199,6 +199,11 @@ int b200pt_set_stream(b200pt_context* ctx, void* cuda_stream);
  * band-major buffer (float offset first * TileHeight * W * 3).  (0, 0) = all rows (default after resize).
  * The render is bit-identical to the same rows of a full render. */
 int b200pt_set_tile_row_range(b200pt_context* ctx, int32_t first_tile_row, int32_t num_tile_rows);
+/* The same at tile granularity -- what the reference enqueues per work-queue entry
+ * (AddWorkQueueEntry_Custom(&WorkData[FlatTileIndex]), ..._optimization_v4.cpp:1714-1718): restrict
+ * render calls to the tiles FlatTileIndex in [first, first + count), FlatTileIndex = TileX + NumTilesX *
+ * TileY.  Consecutive flat indices are contiguous in the buffer.  (0, 0) = all tiles. */
+int b200pt_set_tile_range(b200pt_context* ctx, int32_t first_flat_tile, int32_t num_tiles);
 /* ACCUM_SUM epilogue: target *= 1/(total_frames + 1), the value the reference's running average
  * converges to after total_frames render calls on a zeroed buffer */
 int b200pt_finalize_sum(b200pt_context* ctx, int32_t total_frames);

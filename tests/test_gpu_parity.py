@@ -237,6 +237,13 @@ def test_tile_row_bands_assemble_to_the_full_render(oracle):
         assert np.array_equal(r.download_target(), o)
         with pytest.raises(api.B200PTError):
             r.set_tile_row_range(4, 2)
+        # per-tile scheduling, like the reference's work-queue entries (one FlatTileIndex per entry)
+        r.reset()
+        for flat in np.random.default_rng(0).permutation(ntx * nty):
+            r.frame_counter = 0
+            r.set_tile_range(int(flat), 1)
+            r.render_frames(frames)
+        assert np.array_equal(r.download_target(), o)
 
 
 @pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_V3_REDO],
