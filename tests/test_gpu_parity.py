@@ -302,3 +302,38 @@ def test_full_size_bit_exact_vs_oracle(oracle):
         c = r.counters()
     assert np.array_equal(g, o)
     assert (c["paths"], c["segments"], c["escapes"]) == (oc["paths"], oc["segments"], oc["escapes"])
+
+
+def test_randomised_configurations_bit_exact(oracle):
+    """Seeded sweep over resolution, tiling, bounce budget, frame offset, profile and a random
+    pre-existing accumulation state: GPU == oracle, bit for bit."""
+    rng = np.random.default_rng(20260)
+    envs = {1: oracle.synthetic_env(96, 48), 2: oracle.synthetic_env(16, 96)}
+    for trial in range(24):
+        profile = int(rng.choice([0, 1, 2, 3]))
+        ntx, nty = int(rng.integers(1, 5)), int(rng.integers(1, 6))
+        W, H = 8 * ntx * int(rng.integers(1, 7)), nty * int(rng.integers(1, 25))
+        bounces, frames, start = int(rng.integers(0, 13)), int(rng.integers(1, 6)), int(rng.integers(0, 2000))
+        ek, es = 0, 0
+        if profile == 1:
+            ek, es = 1, 0
+        elif profile == 3:
+            ek, es = 1, 1
+        elif profile == 2:
+            ek = int(rng.choice([0, 1, 2]))
+            es = int(rng.choice([1, 2])) if ek else 0
+        env = envs.get(ek)
+        state = (rng.random(W * H * 3) * 2).astype(np.float32)
+        o, oc = oracle.render(profile, W, H, ntx, nty, bounces, frames, first_frame=start + 1, env=env, env_kind=ek,
+                              env_sampler=es, target=state)
+        with make_renderer(profile, bounces, ek, es if ek else api.SAMPLER_RANDOM) as r:
+            if env is not None:
+                r.set_env(env)
+            r.resize(W, H, ntx, nty)
+            r.upload_target(state)
+            r.frame_counter = start
+            r.render_frames(frames)
+            g = r.download_target()
+            c = r.counters()
+        assert np.array_equal(g, o), (trial, profile, W, H, ntx, nty, bounces, frames, start, ek, es)
+        assert (c["segments"], c["escapes"]) == (oc["segments"], oc["escapes"])
