@@ -28,7 +28,9 @@ ABI_SYMBOLS = [
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
     "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
+    "b200pt_eval_portable", "b200pt_check_portable_tiers",
 ]
+FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP = 0, 1, 2, 3, 4
 
 
 class Texture(ctypes.Structure):
@@ -97,6 +99,10 @@ def load_library():
     L.b200pt_present_acquire.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(i32)]
     L.b200pt_download_rng_state.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.b200pt_get_counters.argtypes = [vp, ctypes.POINTER(Counters)]
+    fpp = ctypes.POINTER(ctypes.c_float)
+    L.b200pt_eval_portable.argtypes = [vp, ctypes.c_int, fpp, fpp, fpp, ctypes.c_size_t]
+    L.b200pt_check_portable_tiers.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64),
+                                              ctypes.POINTER(ctypes.c_uint64)]
     L.b200pt_compute_cull_rects.argtypes = [ctypes.c_int, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     _lib = L
     return L
@@ -260,6 +266,25 @@ class Renderer:
         rc = self._lib.b200pt_download_rng_state(self._ctx, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
         self._check(rc, "b200pt_download_rng_state")
         return out
+
+    def eval_portable(self, fn, a, b=None):
+        """parity-mode transcendental `fn` evaluated on the device (b200pt_eval_portable)"""
+        a = np.ascontiguousarray(a, dtype=np.float32)
+        out = np.empty_like(a)
+        fp = ctypes.POINTER(ctypes.c_float)
+        bb = None if b is None else np.ascontiguousarray(b, dtype=np.float32)
+        rc = self._lib.b200pt_eval_portable(self._ctx, int(fn), a.ctypes.data_as(fp), None if bb is None else bb.ctypes.data_as(fp),
+                                            out.ctypes.data_as(fp), ctypes.c_size_t(a.size))
+        self._check(rc, "b200pt_eval_portable")
+        return out
+
+    def check_portable_tiers(self, fn, first, count):
+        """(mismatches, inputs that took the literal path) of b200pt_check_portable_tiers"""
+        bad, lit = ctypes.c_uint64(0), ctypes.c_uint64(0)
+        rc = self._lib.b200pt_check_portable_tiers(self._ctx, int(fn), ctypes.c_uint64(first), ctypes.c_uint64(count),
+                                                   ctypes.byref(bad), ctypes.byref(lit))
+        self._check(rc, "b200pt_check_portable_tiers")
+        return bad.value, lit.value
 
     def counters(self):
         c = Counters()

@@ -720,6 +720,47 @@ int b200pt_download_rng_state(b200pt_context* c, uint32_t* host_dst)
     return B200PT_OK;
 }
 
+int b200pt_eval_portable(b200pt_context* c, int fn, const float* a, const float* b, float* out, size_t n)
+{
+    if (!c || !a || !out || fn < B200PT_FN_SIN || fn > B200PT_FN_EXP || (fn == B200PT_FN_ATAN2 && !b))
+        return B200PT_ERR_INVALID_ARGUMENT;
+    if (n == 0) return B200PT_OK;
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
+    float *da = nullptr, *db = nullptr, *dout = nullptr;
+    cudaError_t e = cudaMalloc(&da, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMalloc(&dout, n * sizeof(float));
+    if (e == cudaSuccess && fn == B200PT_FN_ATAN2) e = cudaMalloc(&db, n * sizeof(float));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(da, a, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess && db) e = cudaMemcpyAsync(db, b, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = launch_eval_portable(fn, da, db, dout, n, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, dout, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(da); cudaFree(db); cudaFree(dout);
+    CUDA_TRY(c, e);
+    return B200PT_OK;
+}
+
+int b200pt_check_portable_tiers(b200pt_context* c, int fn, uint64_t first, uint64_t count, uint64_t* mismatches,
+                                uint64_t* literal_path)
+{
+    if (!c || !mismatches || (fn != B200PT_FN_ATAN2 && fn != B200PT_FN_ASIN)) return B200PT_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
+    unsigned long long* d = nullptr;
+    unsigned long long h[2] = {0, 0};
+    cudaError_t e = cudaMalloc(&d, sizeof(h));
+    if (e == cudaSuccess) e = cudaMemsetAsync(d, 0, sizeof(h), c->stream);
+    if (e == cudaSuccess) e = launch_check_portable_tiers(fn, first, count, d, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d, sizeof(h), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d);
+    CUDA_TRY(c, e);
+    *mismatches = h[0];
+    if (literal_path) *literal_path = h[1];
+    return B200PT_OK;
+}
+
 int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float* rects, int32_t* count)
 {
     if (!rects || !count || width <= 0 || height <= 0 || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_V3_REDO)

@@ -101,17 +101,129 @@ __device__ __forceinline__ double atan2d_portable(double y, double x)
     return copysign(r, y);
 }
 
-__device__ __forceinline__ float atan2f_portable(float y, float x)
+// ---- the literal algorithms of oracle/portable_math.h (second tier; also the test reference) ----
+static __device__ __noinline__ float atan2f_literal(float y, float x)
 {
     return (float)atan2d_portable((double)y, (double)x);
 }
 
-__device__ __forceinline__ float asinf_portable(float v)
+static __device__ __noinline__ float asinf_literal(float v)
 {
     double x = (double)v;
     if (!(fabs(x) <= 1.0)) return __int_as_float(0x7fc00000);
     double c = __dsqrt_rn(__fma_rn(-x, x, 1.0));
     return (float)atan2d_portable(x, c);
+}
+
+// ---- first tier ---------------------------------------------------------------------------
+// The literal algorithms cost ~130-150 instructions each (two IEEE binary64 divisions, a square
+// root, selects on doubles).  Their binary64 result differs from the real atan2 / asin by a few
+// units of 2^-52, and only its rounding to binary32 is used.  The first tier computes the same real
+// number to better than 2^-48 with ~45 instructions (Newton-refined MUFU seeds, one polynomial;
+// coefficients: scripts/gen_minimax.py) and uses its rounding whenever the value keeps a distance of
+// 2^-42 (relative) from every binary32 rounding boundary -- then both tiers round alike.  Otherwise
+// (probability 2^-18 per call), and for zeros, infinities, NaNs and results below 2^-120, the literal
+// algorithm runs.  b200pt_check_portable_tiers() compares the tiers on the device (exhaustively for
+// asin), tests/test_gpu_parity.py compares the result with the oracle.
+__device__ __forceinline__ double rcp_newton(double d)  // d finite, normal, nonzero
+{
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(d));
+    double e = __fma_rn(-d, y, 1.0);
+    y = __fma_rn(y, e, y);
+    e = __fma_rn(-d, y, 1.0);
+    return __fma_rn(y, e, y);
+}
+
+__device__ __forceinline__ double sqrt_newton(double a)  // a in [2^-60, 4]
+{
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    double g = __dmul_rn(a, y), h = __dmul_rn(y, 0.5);
+    double r = __fma_rn(-h, g, 0.5);
+    g = __fma_rn(g, r, g);
+    h = __fma_rn(h, r, h);
+    r = __fma_rn(-h, g, 0.5);
+    return __fma_rn(g, r, g);
+}
+
+// true when rounding the binary64 value d (0 < d < 2^100) to binary32 cannot be changed by an error of
+// 1024 units in its last place: the 29 dropped bits stay away from the half-way pattern, and the
+// result is a normal binary32 number
+__device__ __forceinline__ bool rounds_safely(double d)
+{
+    const unsigned lo = (unsigned)__double2loint(d), hi = (unsigned)__double2hiint(d);
+    const unsigned dropped = lo & 0x1FFFFFFFu;
+    return (dropped - (0x10000000u - 1024u)) > 2048u && hi >= 0x38700000u;  // |d| >= 2^-120
+}
+
+__device__ __forceinline__ float atan2f_portable(float yf, float xf)
+{
+    const double PI = 3.14159265358979311600e+00, PIO2 = 1.57079632679489655800e+00;
+    const double x = (double)xf, y = (double)yf;
+    const double ax = fabs(x), ay = fabs(y);
+    const double sum = __dadd_rn(ax, ay);
+    if (sum > 0.0 && sum < __longlong_as_double(0x7ff0000000000000LL)) {  // finite, not both zero, no NaN
+        const bool steep = ay > ax;
+        const double mx = steep ? ay : ax, mn = steep ? ax : ay;
+        const double t = __dmul_rn(mn, rcp_newton(mx));  // [0, 1]
+        const double u = __dmul_rn(t, t);
+        double p = 2.96963566016577910e-05;
+        p = __fma_rn(u, p, -3.14200773668073339e-04);
+        p = __fma_rn(u, p, 1.57394932417557619e-03);
+        p = __fma_rn(u, p, -5.00036645373264955e-03);
+        p = __fma_rn(u, p, 1.14300236750545080e-02);
+        p = __fma_rn(u, p, -2.03308700330274601e-02);
+        p = __fma_rn(u, p, 2.99240529380271104e-02);
+        p = __fma_rn(u, p, -3.85260683461067371e-02);
+        p = __fma_rn(u, p, 4.56687247194499449e-02);
+        p = __fma_rn(u, p, -5.20258292466982061e-02);
+        p = __fma_rn(u, p, 5.86777600170671904e-02);
+        p = __fma_rn(u, p, -6.66400760765404609e-02);
+        p = __fma_rn(u, p, 7.69195041879679464e-02);
+        p = __fma_rn(u, p, -9.09087510009998212e-02);
+        p = __fma_rn(u, p, 1.11111089472156838e-01);
+        p = __fma_rn(u, p, -1.42857142011534849e-01);
+        p = __fma_rn(u, p, 1.99999999982444054e-01);
+        p = __fma_rn(u, p, -3.33333333333187987e-01);
+        p = __fma_rn(u, p, 9.99999999999999778e-01);  // atan(t)/t, degree 18 in u = t^2, error < 2^-51
+        double r = __dmul_rn(t, p);
+        if (steep) r = __dsub_rn(PIO2, r);
+        if (__float_as_int(xf) < 0) r = __dsub_rn(PI, r);  // signbit(x), -0 included
+        if (rounds_safely(r)) return copysignf(__double2float_rn(r), yf);
+    }
+    return atan2f_literal(yf, xf);
+}
+
+__device__ __forceinline__ float asinf_portable(float v)
+{
+    const double PIO2 = 1.57079632679489655800e+00;
+    const double ax = fabs((double)v);
+    if (ax < 1.0) {  // |v| == 1, |v| > 1 and NaN: literal algorithm
+        const bool big = ax > 0.5;  // asin(x) = pi/2 - 2 asin(sqrt((1 - x) / 2))
+        double u = __dmul_rn(ax, ax), t = ax;
+        if (big) {
+            u = __fma_rn(ax, -0.5, 0.5);  // exact
+            t = sqrt_newton(u);
+        }
+        double p = 2.87578513674215663e-02;
+        p = __fma_rn(u, p, -1.48518870712472037e-02);
+        p = __fma_rn(u, p, 1.74008794426940214e-02);
+        p = __fma_rn(u, p, 5.45750671864035815e-03);
+        p = __fma_rn(u, p, 1.03228143501857793e-02);
+        p = __fma_rn(u, p, 1.14791774151849057e-02);
+        p = __fma_rn(u, p, 1.39712129735529329e-02);
+        p = __fma_rn(u, p, 1.73523927208699726e-02);
+        p = __fma_rn(u, p, 2.23721729421498886e-02);
+        p = __fma_rn(u, p, 3.03819441385312465e-02);
+        p = __fma_rn(u, p, 4.46428571463554288e-02);
+        p = __fma_rn(u, p, 7.49999999999843292e-02);
+        p = __fma_rn(u, p, 1.66666666666666685e-01);  // (asin(t) - t)/t^3, degree 12 in u = t^2 <= 1/4, error < 2^-52
+        double r = __fma_rn(__dmul_rn(t, u), p, t);  // asin(t) = t + t^3 P(t^2)
+        if (big) r = __fma_rn(r, -2.0, PIO2);
+        if (rounds_safely(r)) return copysignf(__double2float_rn(r), v);
+    }
+    return asinf_literal(v);
 }
 
 // exp of a binary32 argument (v3_redo absorption): k = rint(x / ln 2), two-part reduction, degree-13

@@ -26,4 +26,88 @@ cudaError_t occupancy_parity(const LaunchConfig& lc, int* blocks_per_sm)
     });
 }
 
+// ---- parity hooks for the portable transcendentals (pm_math.cuh) ----------------------------
+// op: 0 sin, 1 cos, 2 atan2(a, b), 3 asin, 4 exp -- exactly what ParityMath hands the megakernel
+__global__ void eval_portable_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float r, t;
+        switch (op) {
+        case 0: ParityMath::sincos(a[i], &r, &t); break;
+        case 1: ParityMath::sincos(a[i], &t, &r); break;
+        case 2: r = ParityMath::atan2(a[i], b[i]); break;
+        case 3: r = ParityMath::asin(a[i]); break;
+        default: r = ParityMath::exp(a[i]); break;
+        }
+        out[i] = r;
+    }
+}
+
+__device__ __forceinline__ uint32_t mix32(uint64_t v)
+{
+    v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
+    return (uint32_t)v;
+}
+
+// Compares the two tiers of atan2f_portable / asinf_portable on generated inputs.  asin (op 3): input
+// number i is the binary32 value with bit pattern (uint32)i -- first = 0, count = 2^32 is exhaustive.
+// atan2 (op 2): pairs hashed from i; every fourth pair is two arbitrary bit patterns (NaN, infinities,
+// denormals included), the others are components of direction-like vectors in [-1, 1], some exactly 0.
+// counts[0] = inputs whose tiers disagree (bit patterns compared, NaNs as NaNs), counts[1] = inputs
+// the first tier handed to the literal algorithm
+__global__ void check_portable_tiers_kernel(int op, unsigned long long first, unsigned long long count, unsigned long long* counts)
+{
+    unsigned long long bad = 0, second = 0;
+    for (unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x; i < count;
+         i += (unsigned long long)gridDim.x * blockDim.x) {
+        const unsigned long long k = first + i;
+        float got, want;
+        if (op == 3) {
+            const float v = __uint_as_float((uint32_t)k);
+            got = pm::asinf_portable(v);
+            want = pm::asinf_literal(v);
+            const double ax = fabs((double)v);
+            second += !(ax < 1.0);
+        } else {
+            const uint32_t h0 = mix32(2 * k), h1 = mix32(2 * k + 1);
+            float y, x;
+            if ((k & 3) == 3) {
+                y = __uint_as_float(h0);
+                x = __uint_as_float(h1);
+            } else {
+                y = (float)(int)(h0 >> 8) * (1.f / 8388608.f) - 1.f;
+                x = (float)(int)(h1 >> 8) * (1.f / 8388608.f) - 1.f;
+                if ((h0 & 0xff) == 0) y = 0.f;
+                if ((h1 & 0xff) == 0) x = -0.f;
+                if ((h1 & 0xff) == 1) x = y;
+            }
+            got = pm::atan2f_portable(y, x);
+            want = pm::atan2f_literal(y, x);
+        }
+        const bool same = (__float_as_uint(got) == __float_as_uint(want)) || (got != got && want != want);
+        bad += !same;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        bad += __shfl_xor_sync(0xffffffffu, bad, o);
+        second += __shfl_xor_sync(0xffffffffu, second, o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+        if (bad) atomicAdd(&counts[0], bad);
+        if (second) atomicAdd(&counts[1], second);
+    }
+}
+
+cudaError_t launch_eval_portable(int op, const float* a, const float* b, float* out, size_t n, cudaStream_t stream)
+{
+    eval_portable_kernel<<<148 * 8, 256, 0, stream>>>(op, a, b, out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_check_portable_tiers(int op, unsigned long long first, unsigned long long count, unsigned long long* counts,
+                                        cudaStream_t stream)
+{
+    check_portable_tiers_kernel<<<148 * 8, 256, 0, stream>>>(op, first, count, counts);
+    return cudaGetLastError();
+}
+
 }  // namespace b200pt

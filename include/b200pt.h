@@ -212,6 +212,18 @@ int b200pt_finalize_sum(b200pt_context* ctx, int32_t total_frames);
  * (row-major W*H, row 0 = top); checks wang_hash stream parity bit for bit */
 int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
 
+/* debug/parity hooks for the parity-mode transcendentals (the stand-ins for the reference's SVML calls,
+ * mathlib.h:449-499).  eval: out[i] = f(a[i] [, b[i]]) computed on the device exactly as the parity kernels
+ * do; host buffers; b is only read by ATAN2 (atan2(a, b)).  check_tiers: the device compares the short
+ * first-tier evaluation of ATAN2 / ASIN against the literal algorithm on `count` generated inputs starting
+ * at number `first` (ASIN: input i = the binary32 bit pattern i, so first 0 / count 2^32 is exhaustive;
+ * ATAN2: hashed pairs) and returns how many results differ (must be 0) and how many inputs took the
+ * literal path. */
+enum { B200PT_FN_SIN = 0, B200PT_FN_COS = 1, B200PT_FN_ATAN2 = 2, B200PT_FN_ASIN = 3, B200PT_FN_EXP = 4 };
+int b200pt_eval_portable(b200pt_context* ctx, int fn, const float* a, const float* b, float* out, size_t n);
+int b200pt_check_portable_tiers(b200pt_context* ctx, int fn, uint64_t first, uint64_t count, uint64_t* mismatches,
+                                uint64_t* literal_path);
+
 /* Host-only helper (no GPU needed): the conservative fragCoord-space rectangles (x0, y0, x1, y1;
  * y = flipped row index) outside of which a camera ray of `profile` cannot hit the scene; the kernel
  * skips the scene trace for such pixels.  rects must hold 4 * 12 floats; *count < 0 = no culling. */

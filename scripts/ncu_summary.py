@@ -34,22 +34,30 @@ else:
     cubins = [binary]
 sass = None
 for cb in cubins:
-    out = subprocess.run(["nvdisasm", "-g", cb], capture_output=True, text=True).stdout.splitlines()
+    out = subprocess.run(["nvdisasm", "-gi", cb], capture_output=True, text=True).stdout.splitlines()
     st = [i for i, l in enumerate(out) if l.startswith(".text." + kprefix)]
     if st:
         en = [i for i, l in enumerate(out) if i > st[0] and l.strip().startswith(".section")]
         sass = out[st[0]:(en[0] if en else len(out))]
         break
-cur, off2 = None, {}
+# nvdisasm -gi prints, before an instruction, the inline chain leaf first: 'File F, line N inlined at G, line M'
+# then the frame (G, M) itself ... down to the line of the kernel body; chain[0] = leaf, chain[-1] = root
+cur, chain, off2, offchain, fresh = None, [], {}, {}, True
 for ln in sass:
     m = re.search(r'//## File "([^"]+)", line (\d+)', ln)
-    if m: cur = (m.group(1).split('/')[-1], int(m.group(2))); continue
+    if m:
+        if fresh: chain = []; fresh = False
+        chain.append((m.group(1).split('/')[-1], int(m.group(2))))
+        cur = chain[0]
+        continue
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*);', ln)
-    if m: off2[int(m.group(1), 16)] = (cur, m.group(2).strip())
+    if m:
+        off2[int(m.group(1), 16)] = (cur, m.group(2).strip()); offchain[int(m.group(1), 16)] = tuple(chain); fresh = True
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(src.splitlines()))
 h = rows[1]; ia, ii, it, isamp = h.index('Address'), h.index('Instructions Executed'), h.index('Thread Instructions Executed'), h.index('# Samples')
 base = None; by = collections.defaultdict(lambda: [0, 0, 0]); tot = [0, 0, 0]
+bysite = [collections.defaultdict(lambda: [0, 0, 0]) for _ in range(3)]  # frames counted from the kernel body
 for r in rows[2:]:
     a = int(r[ia], 16)
     if base is None: base = a
@@ -57,6 +65,10 @@ for r in rows[2:]:
     key = cur if cur else ('?', 0)
     inst, th, sm = int(r[ii]), int(r[it]), int(r[isamp])
     b = by[key]; b[0] += inst; b[1] += th; b[2] += sm
+    ch = [c for c in offchain.get(a - base, ()) if c[0].endswith('.cuh') or c[0].endswith('.cu')]
+    for lvl in range(3):
+        k2 = tuple(reversed(ch[-(lvl + 1):])) if ch else (('?', 0),)
+        b = bysite[lvl][k2]; b[0] += inst; b[1] += th; b[2] += sm
     tot[0] += inst; tot[1] += th; tot[2] += sm
 cache = {}
 def srcline(f, l):
@@ -71,4 +83,9 @@ with open(outp + "_hotspots.txt", "w") as f:
     f.write('by source line (share of warp-level instructions issued, avg active threads, share of stall samples)\n')
     for key, b in sorted(by.items(), key=lambda kv: -kv[1][0])[:60]:
         f.write('%-16s:%4d inst%%=%5.2f eff=%5.1f samp%%=%5.2f | %s\n' % (key[0], key[1], 100 * b[0] / tot[0], b[1] / max(b[0], 1), 100 * b[2] / max(tot[2], 1), srcline(*key)))
+    for lvl in range(3):
+        f.write('\nby call site, %d frame(s) below the kernel body (root first)\n' % lvl)
+        for key, b in sorted(bysite[lvl].items(), key=lambda kv: -kv[1][0])[:(20, 45, 70)[lvl]]:
+            f.write('%-34s inst%%=%5.2f eff=%5.1f samp%%=%5.2f | %s\n' % ('>'.join('%d' % k[1] for k in key), 100 * b[0] / tot[0], b[1] / max(b[0], 1),
+                                                                       100 * b[2] / max(tot[2], 1), srcline(*key[-1])))
 print(open(outp + "_hotspots.txt").read())
