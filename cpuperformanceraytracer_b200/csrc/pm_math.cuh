@@ -13,32 +13,33 @@
 namespace b200pt {
 namespace pm {
 
+// Polynomial coefficients live in constant memory: a DFMA takes a constant-bank operand directly,
+// while a binary64 literal costs two extra (uniform-datapath) move instructions per use.
+// fdlibm __kernel_sin / __kernel_cos minimax coefficients, |r| <= pi/4
+static __constant__ double c_ksin[6] = {-1.66666666666666324348e-01, 8.33333333332248946124e-03, -1.98412698298579493134e-04,
+                                        2.75573137070700676789e-06,  -2.50507602534068634195e-08, 1.58969099521155010221e-10};
+static __constant__ double c_kcos[6] = {4.16666666666666019037e-02, -1.38888888888741095749e-03, 2.48015872894767294178e-05,
+                                        -2.75573143513906633035e-07, 2.08757232129817482790e-09, -1.13596475577881948265e-11};
+
 __device__ __forceinline__ double ksin(double r)
 {
-    // fdlibm __kernel_sin minimax coefficients, |r| <= pi/4
-    const double S1 = -1.66666666666666324348e-01, S2 = 8.33333333332248946124e-03,
-                 S3 = -1.98412698298579493134e-04, S4 = 2.75573137070700676789e-06,
-                 S5 = -2.50507602534068634195e-08, S6 = 1.58969099521155010221e-10;
     double z = __dmul_rn(r, r);
-    double p = __fma_rn(z, S6, S5);
-    p = __fma_rn(z, p, S4);
-    p = __fma_rn(z, p, S3);
-    p = __fma_rn(z, p, S2);
-    p = __fma_rn(z, p, S1);
+    double p = __fma_rn(z, c_ksin[5], c_ksin[4]);
+    p = __fma_rn(z, p, c_ksin[3]);
+    p = __fma_rn(z, p, c_ksin[2]);
+    p = __fma_rn(z, p, c_ksin[1]);
+    p = __fma_rn(z, p, c_ksin[0]);
     return __fma_rn(__dmul_rn(r, z), p, r);
 }
 
 __device__ __forceinline__ double kcos(double r)
 {
-    const double C1 = 4.16666666666666019037e-02, C2 = -1.38888888888741095749e-03,
-                 C3 = 2.48015872894767294178e-05, C4 = -2.75573143513906633035e-07,
-                 C5 = 2.08757232129817482790e-09, C6 = -1.13596475577881948265e-11;
     double z = __dmul_rn(r, r);
-    double p = __fma_rn(z, C6, C5);
-    p = __fma_rn(z, p, C4);
-    p = __fma_rn(z, p, C3);
-    p = __fma_rn(z, p, C2);
-    p = __fma_rn(z, p, C1);
+    double p = __fma_rn(z, c_kcos[5], c_kcos[4]);
+    p = __fma_rn(z, p, c_kcos[3]);
+    p = __fma_rn(z, p, c_kcos[2]);
+    p = __fma_rn(z, p, c_kcos[1]);
+    p = __fma_rn(z, p, c_kcos[0]);
     return __fma_rn(__dmul_rn(z, z), p, __fma_rn(z, -0.5, 1.0));
 }
 
@@ -125,6 +126,22 @@ static __device__ __noinline__ float asinf_literal(float v)
 // (probability 2^-18 per call), and for zeros, infinities, NaNs and results below 2^-120, the literal
 // algorithm runs.  b200pt_check_portable_tiers() compares the tiers on the device (exhaustively for
 // asin), tests/test_gpu_parity.py compares the result with the oracle.
+// atan(t)/t on [0, 1], degree 18 in u = t^2 (error < 2^-51), lowest power first
+static __constant__ double c_atan[19] = {
+    9.99999999999999778e-01, -3.33333333333187987e-01, 1.99999999982444054e-01, -1.42857142011534849e-01,
+    1.11111089472156838e-01, -9.09087510009998212e-02, 7.69195041879679464e-02, -6.66400760765404609e-02,
+    5.86777600170671904e-02, -5.20258292466982061e-02, 4.56687247194499449e-02, -3.85260683461067371e-02,
+    2.99240529380271104e-02, -2.03308700330274601e-02, 1.14300236750545080e-02, -5.00036645373264955e-03,
+    1.57394932417557619e-03, -3.14200773668073339e-04, 2.96963566016577910e-05,
+};
+// (asin(t) - t)/t^3 on [0, 1/2], degree 12 in u = t^2 (error < 2^-52), lowest power first
+static __constant__ double c_asin[13] = {
+    1.66666666666666685e-01, 7.49999999999843292e-02, 4.46428571463554288e-02, 3.03819441385312465e-02,
+    2.23721729421498886e-02, 1.73523927208699726e-02, 1.39712129735529329e-02, 1.14791774151849057e-02,
+    1.03228143501857793e-02, 5.45750671864035815e-03, 1.74008794426940214e-02, -1.48518870712472037e-02,
+    2.87578513674215663e-02,
+};
+
 __device__ __forceinline__ double rcp_newton(double d)  // d finite, normal, nonzero
 {
     double y;
@@ -162,31 +179,31 @@ __device__ __forceinline__ float atan2f_portable(float yf, float xf)
     const double PI = 3.14159265358979311600e+00, PIO2 = 1.57079632679489655800e+00;
     const double x = (double)xf, y = (double)yf;
     const double ax = fabs(x), ay = fabs(y);
-    const double sum = __dadd_rn(ax, ay);
-    if (sum > 0.0 && sum < __longlong_as_double(0x7ff0000000000000LL)) {  // finite, not both zero, no NaN
+    const unsigned ux = __float_as_uint(xf) & 0x7fffffffu, uy = __float_as_uint(yf) & 0x7fffffffu;
+    if (max(ux, uy) - 1u < 0x7f7fffffu) {  // both finite (no NaN), not both zero
         const bool steep = ay > ax;
         const double mx = steep ? ay : ax, mn = steep ? ax : ay;
         const double t = __dmul_rn(mn, rcp_newton(mx));  // [0, 1]
         const double u = __dmul_rn(t, t);
-        double p = 2.96963566016577910e-05;
-        p = __fma_rn(u, p, -3.14200773668073339e-04);
-        p = __fma_rn(u, p, 1.57394932417557619e-03);
-        p = __fma_rn(u, p, -5.00036645373264955e-03);
-        p = __fma_rn(u, p, 1.14300236750545080e-02);
-        p = __fma_rn(u, p, -2.03308700330274601e-02);
-        p = __fma_rn(u, p, 2.99240529380271104e-02);
-        p = __fma_rn(u, p, -3.85260683461067371e-02);
-        p = __fma_rn(u, p, 4.56687247194499449e-02);
-        p = __fma_rn(u, p, -5.20258292466982061e-02);
-        p = __fma_rn(u, p, 5.86777600170671904e-02);
-        p = __fma_rn(u, p, -6.66400760765404609e-02);
-        p = __fma_rn(u, p, 7.69195041879679464e-02);
-        p = __fma_rn(u, p, -9.09087510009998212e-02);
-        p = __fma_rn(u, p, 1.11111089472156838e-01);
-        p = __fma_rn(u, p, -1.42857142011534849e-01);
-        p = __fma_rn(u, p, 1.99999999982444054e-01);
-        p = __fma_rn(u, p, -3.33333333333187987e-01);
-        p = __fma_rn(u, p, 9.99999999999999778e-01);  // atan(t)/t, degree 18 in u = t^2, error < 2^-51
+        double p = c_atan[18];
+        p = __fma_rn(u, p, c_atan[17]);
+        p = __fma_rn(u, p, c_atan[16]);
+        p = __fma_rn(u, p, c_atan[15]);
+        p = __fma_rn(u, p, c_atan[14]);
+        p = __fma_rn(u, p, c_atan[13]);
+        p = __fma_rn(u, p, c_atan[12]);
+        p = __fma_rn(u, p, c_atan[11]);
+        p = __fma_rn(u, p, c_atan[10]);
+        p = __fma_rn(u, p, c_atan[9]);
+        p = __fma_rn(u, p, c_atan[8]);
+        p = __fma_rn(u, p, c_atan[7]);
+        p = __fma_rn(u, p, c_atan[6]);
+        p = __fma_rn(u, p, c_atan[5]);
+        p = __fma_rn(u, p, c_atan[4]);
+        p = __fma_rn(u, p, c_atan[3]);
+        p = __fma_rn(u, p, c_atan[2]);
+        p = __fma_rn(u, p, c_atan[1]);
+        p = __fma_rn(u, p, c_atan[0]);
         double r = __dmul_rn(t, p);
         if (steep) r = __dsub_rn(PIO2, r);
         if (__float_as_int(xf) < 0) r = __dsub_rn(PI, r);  // signbit(x), -0 included
@@ -206,19 +223,19 @@ __device__ __forceinline__ float asinf_portable(float v)
             u = __fma_rn(ax, -0.5, 0.5);  // exact
             t = sqrt_newton(u);
         }
-        double p = 2.87578513674215663e-02;
-        p = __fma_rn(u, p, -1.48518870712472037e-02);
-        p = __fma_rn(u, p, 1.74008794426940214e-02);
-        p = __fma_rn(u, p, 5.45750671864035815e-03);
-        p = __fma_rn(u, p, 1.03228143501857793e-02);
-        p = __fma_rn(u, p, 1.14791774151849057e-02);
-        p = __fma_rn(u, p, 1.39712129735529329e-02);
-        p = __fma_rn(u, p, 1.73523927208699726e-02);
-        p = __fma_rn(u, p, 2.23721729421498886e-02);
-        p = __fma_rn(u, p, 3.03819441385312465e-02);
-        p = __fma_rn(u, p, 4.46428571463554288e-02);
-        p = __fma_rn(u, p, 7.49999999999843292e-02);
-        p = __fma_rn(u, p, 1.66666666666666685e-01);  // (asin(t) - t)/t^3, degree 12 in u = t^2 <= 1/4, error < 2^-52
+        double p = c_asin[12];
+        p = __fma_rn(u, p, c_asin[11]);
+        p = __fma_rn(u, p, c_asin[10]);
+        p = __fma_rn(u, p, c_asin[9]);
+        p = __fma_rn(u, p, c_asin[8]);
+        p = __fma_rn(u, p, c_asin[7]);
+        p = __fma_rn(u, p, c_asin[6]);
+        p = __fma_rn(u, p, c_asin[5]);
+        p = __fma_rn(u, p, c_asin[4]);
+        p = __fma_rn(u, p, c_asin[3]);
+        p = __fma_rn(u, p, c_asin[2]);
+        p = __fma_rn(u, p, c_asin[1]);
+        p = __fma_rn(u, p, c_asin[0]);
         double r = __fma_rn(__dmul_rn(t, u), p, t);  // asin(t) = t + t^3 P(t^2)
         if (big) r = __fma_rn(r, -2.0, PIO2);
         if (rounds_safely(r)) return copysignf(__double2float_rn(r), v);
