@@ -473,6 +473,7 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     rp.cameraDistance = c->cameraDistance;
     rp.rcp_width = 1.0f / (float)c->width;
     rp.rcp_height = 1.0f / (float)c->height;
+    rp.aspect = (float)c->width / (float)c->height;
     {
         // significant bits of an integer = bit length minus trailing zeros
         auto sig_bits = [](unsigned v) { int len = 0, tz = 0; for (unsigned t = v; t; t >>= 1) len++; while (v && !(v & 1u)) { v >>= 1; tz++; } return len - tz; };

@@ -43,22 +43,22 @@ __device__ __forceinline__ double kcos(double r)
     return __fma_rn(__dmul_rn(z, z), p, __fma_rn(z, -0.5, 1.0));
 }
 
+static __constant__ double c_reduce[4] = {6.36619772367581382433e-01 /* 2/pi */, 1.57079632673412561417e+00 /* pi/2 hi */,
+                                          6.07710050650619224932e-11 /* pi/2 lo */, 0.0};
+
 __device__ __forceinline__ void sincosf_portable(float a, float* s_out, float* c_out)
 {
-    const double PIO2_HI = 1.57079632673412561417e+00, PIO2_LO = 6.07710050650619224932e-11;
-    const double TWO_OVER_PI = 6.36619772367581382433e-01;
     double x = (double)a;
-    double kd = rint(__dmul_rn(x, TWO_OVER_PI));
-    double r = __fma_rn(-kd, PIO2_HI, x);
-    r = __fma_rn(-kd, PIO2_LO, r);
+    double kd = rint(__dmul_rn(x, c_reduce[0]));
+    double r = __fma_rn(-kd, c_reduce[1], x);
+    r = __fma_rn(-kd, c_reduce[2], r);
     int k = (int)kd;
-    double s = ksin(r), c = kcos(r);
-    double ss = (k & 1) ? c : s;
-    double cc = (k & 1) ? s : c;
-    if (k & 2) ss = -ss;
-    if ((k + 1) & 2) cc = -cc;
-    *s_out = (float)ss;
-    *c_out = (float)cc;
+    // quadrant bookkeeping on the rounded binary32 values: rounding commutes with swapping and with negation
+    const float s = __double2float_rn(ksin(r)), c = __double2float_rn(kcos(r));
+    const float ss = (k & 1) ? c : s;
+    const float cc = (k & 1) ? s : c;
+    *s_out = __uint_as_float(__float_as_uint(ss) ^ (((unsigned)k << 30) & 0x80000000u));        // k & 2: negate
+    *c_out = __uint_as_float(__float_as_uint(cc) ^ (((unsigned)(k + 1) << 30) & 0x80000000u));  // (k + 1) & 2
 }
 
 __device__ __forceinline__ double atan01(double t)

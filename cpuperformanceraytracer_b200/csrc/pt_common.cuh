@@ -118,6 +118,7 @@ struct RenderParams {
     int num_bounces;
     float cameraDistance;     // 1 / tan(FOV/2), computed on the host like v2.cpp:546
     float rcp_width, rcp_height;  // RN(1/W), RN(1/H), host-computed
+    float aspect;             // RN(W/H): aspectRatio of mainImage (v2.cpp:556), host-computed
     int res_div_exact;        // W and H have <= 16 significant bits: x / W == fma(fma(-q, W, x), rcp, q), q = x * rcp
     // conservative screen-space bounds of the scene's primitives in fragCoord space
     // (x0, y0, x1, y1; y = flipped row): a pixel whose jitter footprint overlaps none of them cannot
