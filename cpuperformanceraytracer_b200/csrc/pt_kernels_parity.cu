@@ -51,6 +51,7 @@ __device__ __forceinline__ uint32_t mix32(uint64_t v)
 
 // Compares the two tiers of atan2f_portable / asinf_portable on generated inputs.  asin (op 3): input
 // number i is the binary32 value with bit pattern (uint32)i -- first = 0, count = 2^32 is exhaustive.
+// sqrt / rcp (ops 5, 6): same enumeration, the unchecked mid-range forms against __fsqrt_rn / __frcp_rn.
 // atan2 (op 2): pairs hashed from i; every fourth pair is two arbitrary bit patterns (NaN, infinities,
 // denormals included), the others are components of direction-like vectors in [-1, 1], some exactly 0.
 // counts[0] = inputs whose tiers disagree (bit patterns compared, NaNs as NaNs), counts[1] = inputs
@@ -62,7 +63,13 @@ __global__ void check_portable_tiers_kernel(int op, unsigned long long first, un
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long k = first + i;
         float got, want;
-        if (op == 3) {
+        if (op == 5 || op == 6) {  // sqrt_mid / rcp_mid against the checked forms, positive operands in [2^-60, 2^60]
+            const float v = __uint_as_float((uint32_t)k);
+            const bool in_range = v >= 8.67361737988403547e-19f && v <= 1.15292150460684698e+18f;
+            got = in_range ? (op == 5 ? ParityMath::sqrt_mid(v) : ParityMath::rcp_mid(v)) : 0.f;
+            want = in_range ? (op == 5 ? ParityMath::sqrt(v) : ParityMath::rcp(v)) : 0.f;
+            second += !in_range;
+        } else if (op == 3) {
             const float v = __uint_as_float((uint32_t)k);
             got = pm::asinf_portable(v);
             want = pm::asinf_literal(v);

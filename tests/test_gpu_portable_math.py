@@ -74,3 +74,13 @@ def test_first_tier_never_changes_a_result():
         assert bad == 0
         bad, _ = r.check_portable_tiers(api.FN_ATAN2, 2 ** 40, 2 ** 30)
         assert bad == 0
+
+
+def test_unchecked_sqrt_and_rcp_sequences_are_the_ieee_operations():
+    """every binary32 operand in [2^-60, 2^60]: sqrt_mid == __fsqrt_rn, rcp_mid == __frcp_rn"""
+    in_range = ((0x5D800000 - 0x21800000) + 1)  # bit patterns from 2^-60 to 2^60 inclusive
+    with api.Renderer(profile=api.PROFILE_V2) as r:
+        for fn in (api.FN_SQRT, api.FN_RCP):
+            bad, skipped = r.check_portable_tiers(fn, 0, 2 ** 32)
+            assert bad == 0
+            assert skipped == 2 ** 32 - in_range
