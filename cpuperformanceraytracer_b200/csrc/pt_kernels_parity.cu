@@ -63,12 +63,26 @@ __global__ void check_portable_tiers_kernel(int op, unsigned long long first, un
          i += (unsigned long long)gridDim.x * blockDim.x) {
         const unsigned long long k = first + i;
         float got, want;
-        if (op == 5 || op == 6) {  // sqrt_mid / rcp_mid against the checked forms, positive operands in [2^-60, 2^60]
-            const float v = __uint_as_float((uint32_t)k);
-            const bool in_range = v >= 8.67361737988403547e-19f && v <= 1.15292150460684698e+18f;
+        if (op == 5 || op == 6) {  // sqrt_mid / rcp_mid against the checked forms over their whole valid range
+            const uint32_t bits = (uint32_t)k, mag = bits & 0x7fffffffu;
+            const float v = __uint_as_float(bits);
+            const bool in_range = op == 5 ? (bits >= 0x0d000000u && bits <= 0x7f7fffffu)   // [2^-101, FLT_MAX]
+                                          : (mag >= 0x00800000u && mag < 0x7e800000u);    // 2^-126 <= |v| < 2^126
             got = in_range ? (op == 5 ? ParityMath::sqrt_mid(v) : ParityMath::rcp_mid(v)) : 0.f;
             want = in_range ? (op == 5 ? ParityMath::sqrt(v) : ParityMath::rcp(v)) : 0.f;
             second += !in_range;
+        } else if (op == 7) {  // div_mid against __fdiv_rn: hashed pairs, |a| in [2^-60, 2^60] or 0, |b| in [2^-60, 2^60]
+            const uint32_t h0 = mix32(2 * k), h1 = mix32(2 * k + 1);
+            const uint32_t ea = 67u + (h0 >> 8) % 121u, eb = 67u + (h1 >> 8) % 121u;  // exponent fields 67..187
+            float a = __uint_as_float((h0 & 0x80000000u) | (ea << 23) | (mix32(k ^ 0x9e3779b97f4a7c15ULL) & 0x7fffffu));
+            float b = __uint_as_float((h1 & 0x80000000u) | (eb << 23) | (mix32(k + 0x51ed270b7f4a7c15ULL) & 0x7fffffu));
+            if ((k & 7) == 1) b = (k & 8) ? 1.77777779f : 1.33333337f;  // 16:9, 4:3
+            if ((h0 & 0xff) == 0) {  // +0 / positive
+                a = 0.f;
+                b = fabsf(b);
+            }
+            got = ParityMath::div_mid(a, b, ParityMath::div_mid_reciprocal(b));
+            want = ParityMath::div(a, b);
         } else if (op == 3) {
             const float v = __uint_as_float((uint32_t)k);
             got = pm::asinf_portable(v);

@@ -219,10 +219,11 @@ int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
  * at number `first` (ASIN: input i = the binary32 bit pattern i, so first 0 / count 2^32 is exhaustive;
  * ATAN2: hashed pairs) and returns how many results differ (must be 0) and how many inputs took the
  * literal path.  SQRT / RCP: the kernels' unchecked square root / reciprocal sequences (used where the
- * operand is known to lie in [2^-60, 2^60]) against the IEEE operations, same enumeration as ASIN;
- * literal_path counts the bit patterns outside that range, which are skipped. */
+ * operand is known to be a normal number of moderate size) against the IEEE operations over their whole
+ * valid range, same enumeration as ASIN; literal_path counts the bit patterns outside the range, which
+ * are skipped.  DIV: the unchecked division sequence against IEEE division on hashed operand pairs. */
 enum { B200PT_FN_SIN = 0, B200PT_FN_COS = 1, B200PT_FN_ATAN2 = 2, B200PT_FN_ASIN = 3, B200PT_FN_EXP = 4,
-       B200PT_FN_SQRT = 5, B200PT_FN_RCP = 6 /* check_tiers only */ };
+       B200PT_FN_SQRT = 5, B200PT_FN_RCP = 6, B200PT_FN_DIV = 7 /* 5-7: check_tiers only */ };
 int b200pt_eval_portable(b200pt_context* ctx, int fn, const float* a, const float* b, float* out, size_t n);
 int b200pt_check_portable_tiers(b200pt_context* ctx, int fn, uint64_t first, uint64_t count, uint64_t* mismatches,
                                 uint64_t* literal_path);

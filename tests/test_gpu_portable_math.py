@@ -76,11 +76,13 @@ def test_first_tier_never_changes_a_result():
         assert bad == 0
 
 
-def test_unchecked_sqrt_and_rcp_sequences_are_the_ieee_operations():
-    """every binary32 operand in [2^-60, 2^60]: sqrt_mid == __fsqrt_rn, rcp_mid == __frcp_rn"""
-    in_range = ((0x5D800000 - 0x21800000) + 1)  # bit patterns from 2^-60 to 2^60 inclusive
+def test_unchecked_sqrt_rcp_div_sequences_are_the_ieee_operations():
+    """every binary32 operand of the valid range: sqrt_mid == __fsqrt_rn, rcp_mid == __frcp_rn; div_mid == __fdiv_rn
+    on 2^33 hashed pairs"""
     with api.Renderer(profile=api.PROFILE_V2) as r:
-        for fn in (api.FN_SQRT, api.FN_RCP):
-            bad, skipped = r.check_portable_tiers(fn, 0, 2 ** 32)
-            assert bad == 0
-            assert skipped == 2 ** 32 - in_range
+        bad, skipped = r.check_portable_tiers(api.FN_SQRT, 0, 2 ** 32)
+        assert bad == 0 and skipped == 2 ** 32 - (0x7F7FFFFF - 0x0D000000 + 1)
+        bad, skipped = r.check_portable_tiers(api.FN_RCP, 0, 2 ** 32)
+        assert bad == 0 and skipped == 2 ** 32 - 2 * (0x7E800000 - 0x00800000)
+        bad, _ = r.check_portable_tiers(api.FN_DIV, 0, 2 ** 33)
+        assert bad == 0
