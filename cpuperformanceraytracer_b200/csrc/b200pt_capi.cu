@@ -115,6 +115,7 @@ LaunchConfig launch_config(const b200pt_context* c)
                                                                                                               : kSamplerPoint;
     lc.accum_mode = c->params.accum_mode;
     lc.static_scene = (c->params.generic_scene_tables || c->custom_scene) ? 0 : 1;
+    if (lc.profile == kProfileV4 && lc.static_scene && !v4_scene_matches_static_tables(c->scenes.v4)) lc.static_scene = 0;
     lc.block = 256;
     lc.grid = 1;
     return lc;

@@ -68,6 +68,35 @@ struct V4Scene {
     float cameraDistance;
 };
 
+// The built-in v4 scene as compile-time knowledge (kernels specialised with STATIC):
+//  * sphere i has centre (-18 + 6 i, -8, 10) and radius 2.8 (v4.cpp:1474-1495): m.y, m.z and the inner terms
+//    of dot(m, d) / dot(m, m) are shared by the seven tests;
+//  * the quads are axis-aligned, so the host-computed vectors of V4Quad have exact zeros.  Bit k of a mask =
+//    component k is nonzero, order n, NxV01, NxV20, NxV02, NxV30.  Products with those zeros are +-0 for a
+//    finite ray, so a dot product reduces to its nonzero terms (same nesting, same roundings; only the sign
+//    of an exactly-zero result can differ, which no comparison below observes).
+//    b200pt_create verifies the masks against the scene it built and falls back to the generic kernel.
+constexpr float kV4SphereY = -8.0f, kV4SphereZ = 10.0f, kV4SphereRadius = 2.8f;
+__host__ __device__ constexpr float v4_sphere_x(int i) { return -18.0f + 6.0f * (float)i; }
+constexpr int kV4QuadMasks[kV4Quads][5] = {{2, 4, 5, 5, 1}, {4, 2, 3, 3, 1}, {2, 4, 5, 5, 1}, {2, 4, 5, 5, 1}};
+inline int v3_nonzero_mask(const v3& v) { return (v.x != 0.f ? 1 : 0) | (v.y != 0.f ? 2 : 0) | (v.z != 0.f ? 4 : 0); }
+// true when `s` is the built-in scene the STATIC v4 kernels assume
+inline bool v4_scene_matches_static_tables(const V4Scene& s)
+{
+    if (s.numQuads != kV4Quads || s.numSpheres != kV4Spheres) return false;
+    for (int i = 0; i < kV4Quads; i++) {
+        const V4Quad& q = s.quad[i];
+        const int m[5] = {v3_nonzero_mask(q.n), v3_nonzero_mask(q.NxV01), v3_nonzero_mask(q.NxV20), v3_nonzero_mask(q.NxV02),
+                          v3_nonzero_mask(q.NxV30)};
+        for (int k = 0; k < 5; k++)
+            if (m[k] != kV4QuadMasks[i][k]) return false;
+    }
+    for (int i = 0; i < kV4Spheres; i++)
+        if (s.sphere[i].x != v4_sphere_x(i) || s.sphere[i].y != kV4SphereY || s.sphere[i].z != kV4SphereZ || s.sphere[i].w != kV4SphereRadius)
+            return false;
+    return true;
+}
+
 // Scene of demofox_path_tracing_v3_redo.cpp, SCENE 1 (:485-600): the v4 geometry tested with the
 // legacy (ScalarTriple) quad test, exact-arithmetic Fresnel materials, a striped backdrop whose
 // albedo is computed at the hit (:511-515), GetZeroedMaterial IOR = 1 for the quads (:155-168).

@@ -112,7 +112,7 @@ void build_v4_scene(V4Scene* s)
     s->mat[3].emissive = muls(mk(1.0f, 0.9f, 0.7f), 20.0f);
     const int c_numSpheres = kV4Spheres;
     for (int i = 0; i < c_numSpheres; i++) {  // v4.cpp:1474-1495
-        const v3 c = add(mk(-18.0f + 6.0f * (float)i, -8.0f, 0.0f), T);
+        const v3 c = add(mk(-18.0f + 6.0f * (float)i, -8.0f, 0.0f), T);  // == (v4_sphere_x(i), kV4SphereY, kV4SphereZ)
         s->sphere[i] = make_float4(c.x, c.y, c.z, 2.8f + 0.0f);
         V4Material& m = s->mat[kV4Quads + i];
         const float r = (((float)i) / (float)(c_numSpheres - 1)) * 0.5f;

@@ -246,15 +246,18 @@ def test_tile_row_bands_assemble_to_the_full_render(oracle):
         assert np.array_equal(r.download_target(), o)
 
 
-@pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_V3_REDO],
-                         ids=["v2", "simt_textured", "v3_redo"])
+@pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_V3_REDO, api.PROFILE_OPT_V4],
+                         ids=["v2", "simt_textured", "v3_redo", "opt_v4"])
 def test_static_scene_specialisation_changes_nothing(oracle, profile):
-    """Quad vertices as immediates (default) vs read from the scene table: identical bits."""
+    """Built-in scene as compile-time knowledge (default: quad vertices / sphere centres as immediates, zero
+    components of the v4 quad tables dropped, unchecked reciprocals for the built-in materials) vs the generic
+    kernel that reads everything from the scene table: identical bits."""
     W, H, ntx, nty, frames = 256, 160, 4, 5, 10
     env = oracle.synthetic_env(128, 64) if profile != api.PROFILE_V2 else None
+    kw = dict(env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM) if profile == api.PROFILE_OPT_V4 else {}
     res = []
     for generic in (False, True):
-        with api.Renderer(profile=profile, num_bounces=8, generic_scene_tables=generic) as r:
+        with api.Renderer(profile=profile, num_bounces=8, generic_scene_tables=generic, **kw) as r:
             if env is not None:
                 r.set_env(env)
             r.resize(W, H, ntx, nty)
