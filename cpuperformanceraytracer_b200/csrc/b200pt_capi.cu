@@ -116,6 +116,15 @@ LaunchConfig launch_config(const b200pt_context* c)
     lc.accum_mode = c->params.accum_mode;
     lc.static_scene = (c->params.generic_scene_tables || c->custom_scene) ? 0 : 1;
     if (lc.profile == kProfileV4 && lc.static_scene && !v4_scene_matches_static_tables(c->scenes.v4)) lc.static_scene = 0;
+    if (lc.static_scene && lc.profile != kProfileV4) {  // the legacy kernels' immediate sphere data must be what the host built
+        const bool v3r = lc.profile == kProfileV3Redo;
+        for (int i = 0; i < (v3r ? kV3Spheres : kCornellSpheres); i++) {
+            const float4 S = v3r ? c->scenes.v3redo.sphere[i] : c->scenes.cornell.sphere[i];
+            const bool same = v3r ? (S.x == v4_sphere_x(i) && S.y == kV4SphereY && S.z == kV4SphereZ && S.w == kV4SphereRadius)
+                                  : (S.x == cornell_sphere_x(i) && S.y == kCornellSphereY && S.z == kCornellSphereZ && S.w == kCornellSphereRadius);
+            if (!same) lc.static_scene = 0;
+        }
+    }
     lc.block = 256;
     lc.grid = 1;
     return lc;

@@ -78,6 +78,9 @@ struct V4Scene {
 //    b200pt_create verifies the masks against the scene it built and falls back to the generic kernel.
 constexpr float kV4SphereY = -8.0f, kV4SphereZ = 10.0f, kV4SphereRadius = 2.8f;
 __host__ __device__ constexpr float v4_sphere_x(int i) { return -18.0f + 6.0f * (float)i; }
+// Cornell spheres (v2.cpp:429-447): centres (-9 | 0 | 9, -9.5, 20) + sceneTranslation, radius 3
+__host__ __device__ constexpr float cornell_sphere_x(int i) { return -9.0f + 9.0f * (float)i; }
+constexpr float kCornellSphereY = -9.5f, kCornellSphereZ = 30.0f, kCornellSphereRadius = 3.0f;
 constexpr int kV4QuadMasks[kV4Quads][5] = {{2, 4, 5, 5, 1}, {4, 2, 3, 3, 1}, {2, 4, 5, 5, 1}, {2, 4, 5, 5, 1}};
 inline int v3_nonzero_mask(const v3& v) { return (v.x != 0.f ? 1 : 0) | (v.y != 0.f ? 2 : 0) | (v.z != 0.f ? 4 : 0); }
 // true when `s` is the built-in scene the STATIC v4 kernels assume
