@@ -30,7 +30,7 @@ ABI_SYMBOLS = [
     "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
     "b200pt_eval_portable", "b200pt_check_portable_tiers",
 ]
-FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP, FN_SQRT, FN_RCP, FN_DIV = 0, 1, 2, 3, 4, 5, 6, 7
+FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP, FN_SQRT, FN_RCP, FN_DIV, FN_EQUIRECT_TEXEL = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 
 class Texture(ctypes.Structure):

@@ -755,7 +755,7 @@ int b200pt_eval_portable(b200pt_context* c, int fn, const float* a, const float*
 int b200pt_check_portable_tiers(b200pt_context* c, int fn, uint64_t first, uint64_t count, uint64_t* mismatches,
                                 uint64_t* literal_path)
 {
-    if (!c || !mismatches || fn < B200PT_FN_ATAN2 || fn > B200PT_FN_DIV || fn == B200PT_FN_EXP) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c || !mismatches || fn < B200PT_FN_ATAN2 || fn > B200PT_FN_EQUIRECT_TEXEL || fn == B200PT_FN_EXP) return B200PT_ERR_INVALID_ARGUMENT;
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     unsigned long long* d = nullptr;

@@ -43,6 +43,8 @@ __global__ void eval_portable_kernel(int op, const float* __restrict__ a, const 
     }
 }
 
+__device__ __forceinline__ float random01_bits(uint32_t h) { return __int2float_rn((int)(h & 0x7FFFFFFFu)) * 4.656612873077392578125e-10f; }
+
 __device__ __forceinline__ uint32_t mix32(uint64_t v)
 {
     v ^= v >> 33; v *= 0xff51afd7ed558ccdULL; v ^= v >> 33; v *= 0xc4ceb9fe1a85ec53ULL; v ^= v >> 33;
@@ -71,6 +73,40 @@ __global__ void check_portable_tiers_kernel(int op, unsigned long long first, un
             got = in_range ? (op == 5 ? ParityMath::sqrt_mid(v) : ParityMath::rcp_mid(v)) : 0.f;
             want = in_range ? (op == 5 ? ParityMath::sqrt(v) : ParityMath::rcp(v)) : 0.f;
             second += !in_range;
+        } else if (op == 8) {  // texel index of the random-jitter equirect lookup: bracketed fast form vs exact angles
+            const uint32_t h0 = mix32(3 * k), h1 = mix32(3 * k + 1), h2 = mix32(3 * k + 2);
+            // a direction: normalised like the kernels do, sometimes axis-aligned / near a pole / a seam
+            float dx = (float)(int)(h0 >> 8) * (1.f / 8388608.f) - 1.f, dy = (float)(int)(h1 >> 8) * (1.f / 8388608.f) - 1.f;
+            float dz = (float)(int)(h2 >> 8) * (1.f / 8388608.f) - 1.f;
+            if ((h0 & 0xff) == 0) dx = 0.f;
+            if ((h1 & 0xff) == 0) dy = 0.f;
+            if ((h2 & 0xff) == 0) dz = 0.f;
+            if ((h0 & 0xff) == 1) { dx *= 1e-4f; dz *= 1e-4f; }   // near a pole
+            if ((h2 & 0xff) == 1) dz *= 1e-6f;                     // near the seam / the centre column
+            const v3 d = normalize3<ParityMath>(mk(dx, dy, dz));
+            const float r1 = random01_bits(mix32(k ^ 0x1234567ULL)), r2 = random01_bits(mix32(k ^ 0x89abcdeULL));
+            RenderParams rp{};
+            const int sizes[4][2] = {{512, 256}, {2048, 1024}, {4096, 2048}, {1000, 333}};
+            rp.env_w = sizes[k & 3][0];
+            rp.env_h = sizes[k & 3][1];
+            const float ux = fract1(fmaf(0.1591f, ParityMath::atan2(d.z, d.x), 0.5f));
+            const float uy = fract1(fmaf(0.3183f, ParityMath::asin(d.y), 0.5f));
+            const float u = saturate1(ux), v = saturate1(uy);
+            const float Row = fmaf(v, (float)rp.env_h, -v), Col = fmaf(u, (float)rp.env_w, -u);
+            const int exact = __float2int_rn(fmaf(floorf(Row + r1), (float)rp.env_w, floorf(Col + r2)));
+            int fast = 0;
+            const bool certain = equirect_random_texel_certain(rp, d, r1, r2, fast);
+            // the brackets rest on |approximate angle - exact angle| < kAngleEps: demand a factor 3 of slack
+            const float ea = fabsf(atan2_approx(d.z, d.x) - ParityMath::atan2(d.z, d.x));
+            float c;
+            const float om = fmaf(-d.y, d.y, 1.f);
+            asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(om));
+            const float eb = fabsf(atan2_approx(d.y, c) - ParityMath::asin(d.y));
+            const bool finite = d.x == d.x && fabsf(d.y) < 1.f && (d.x != 0.f || d.z != 0.f);
+            const bool angles_ok = !finite || (ea < kAngleEps / 3.f && eb < kAngleEps / 3.f);
+            got = (certain && fast != exact) || !angles_ok ? 1.f : 0.f;
+            want = 0.f;
+            second += !certain;
         } else if (op == 7) {  // div_mid against __fdiv_rn: hashed pairs, |a| in [2^-60, 2^60] or 0, |b| in [2^-60, 2^60]
             const uint32_t h0 = mix32(2 * k), h1 = mix32(2 * k + 1);
             const uint32_t ea = 67u + (h0 >> 8) % 121u, eb = 67u + (h1 >> 8) % 121u;  // exponent fields 67..187

@@ -221,9 +221,13 @@ int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
  * literal path.  SQRT / RCP: the kernels' unchecked square root / reciprocal sequences (used where the
  * operand is known to be a normal number of moderate size) against the IEEE operations over their whole
  * valid range, same enumeration as ASIN; literal_path counts the bit patterns outside the range, which
- * are skipped.  DIV: the unchecked division sequence against IEEE division on hashed operand pairs. */
+ * are skipped.  DIV: the unchecked division sequence against IEEE division on hashed operand pairs.
+ * EQUIRECT_TEXEL: the texel index of the random-jitter equirect lookup obtained by bracketing binary32
+ * approximations of the two angles, against the index from the exact angles, on hashed directions / jitters /
+ * map sizes; a mismatch is also counted when an approximate angle strays more than a third of the bracket
+ * half-width from the exact one; literal_path = lookups whose bracket was not decisive. */
 enum { B200PT_FN_SIN = 0, B200PT_FN_COS = 1, B200PT_FN_ATAN2 = 2, B200PT_FN_ASIN = 3, B200PT_FN_EXP = 4,
-       B200PT_FN_SQRT = 5, B200PT_FN_RCP = 6, B200PT_FN_DIV = 7 /* 5-7: check_tiers only */ };
+       B200PT_FN_SQRT = 5, B200PT_FN_RCP = 6, B200PT_FN_DIV = 7, B200PT_FN_EQUIRECT_TEXEL = 8 /* 5-8: check_tiers only */ };
 int b200pt_eval_portable(b200pt_context* ctx, int fn, const float* a, const float* b, float* out, size_t n);
 int b200pt_check_portable_tiers(b200pt_context* ctx, int fn, uint64_t first, uint64_t count, uint64_t* mismatches,
                                 uint64_t* literal_path);
