@@ -104,7 +104,23 @@ __global__ void check_portable_tiers_kernel(int op, unsigned long long first, un
             const float eb = fabsf(atan2_approx(d.y, c) - ParityMath::asin(d.y));
             const bool finite = d.x == d.x && fabsf(d.y) < 1.f && (d.x != 0.f || d.z != 0.f);
             const bool angles_ok = !finite || (ea < kAngleEps / 3.f && eb < kAngleEps / 3.f);
-            got = (certain && fast != exact) || !angles_ok ? 1.f : 0.f;
+            // the point sampler of texture.cpp:101-139 (simt_textured), same direction and map
+            bool point_bad = false;
+            {
+                float px = ParityMath::atan2(d.z, d.x) * 0.1591f, py = ParityMath::asin(d.y) * 0.3183f;
+                px = px + 0.5f;
+                py = py + 0.5f;
+                int point_exact = -1;
+                if (px == px && py == py) {
+                    px -= (float)(int)px;
+                    py -= (float)(int)py;
+                    if (px >= 0.f && px < 1.f && py >= 0.f && py < 1.f)
+                        point_exact = (int)(py * (float)(rp.env_h - 1)) * rp.env_w + (int)(px * (float)(rp.env_w - 1));
+                }
+                int point_fast = 0;
+                if (equirect_point_texel_certain(rp, d, point_fast)) point_bad = point_fast != point_exact;
+            }
+            got = (certain && fast != exact) || !angles_ok || point_bad ? 1.f : 0.f;
             want = 0.f;
             second += !certain;
         } else if (op == 7) {  // div_mid against __fdiv_rn: hashed pairs, |a| in [2^-60, 2^60] or 0, |b| in [2^-60, 2^60]
