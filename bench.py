@@ -159,7 +159,7 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    frames_per_step = 2
+    frames_per_step = 8  # ~1.4 s of the host's cores per step
     base = cpu_reference_run(frames=frames_per_step * args.steps, warmup=frames_per_step * args.warmup)
     paths = WIDTH * HEIGHT * frames_per_step * args.steps
     line = {
@@ -342,7 +342,7 @@ def main():
         }
         if world == 1 and not args.no_cpu_baseline:
             try:
-                cpu_base = cpu_reference_run(frames=8, warmup=2)
+                cpu_base = cpu_reference_run(frames=64, warmup=2)  # ~11 s of CPU work
             except Exception as e:  # the reported baseline must not take the bench down
                 cpu_base = {"value": None, "unit": "Mpaths/s", "cores": 0, "kind": "unavailable", "sample": str(e)[:200]}
         line = {
