@@ -29,8 +29,9 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "
           "-ffp-contract=off", "-I", os.path.join(ROOT, "include")]
 IEEE = ["--fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
 # tuning knob for experiments: minimum resident CTAs per SM handed to __launch_bounds__
-if os.environ.get("B200PT_MIN_BLOCKS"):
-    COMMON = COMMON + ["-DB200PT_MIN_BLOCKS=" + os.environ["B200PT_MIN_BLOCKS"]]
+for _knob in ("B200PT_MIN_BLOCKS_CORNELL", "B200PT_MIN_BLOCKS_V4"):
+    if os.environ.get(_knob):
+        COMMON = COMMON + ["-D%s=%s" % (_knob, os.environ[_knob])]
 
 UNITS = [
     # (source, object, extra flags)
