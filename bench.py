@@ -285,21 +285,25 @@ def main():
     e2e = None
     cpu_base = None
     if world == 1:
-        host = np.zeros(WIDTH * HEIGHT * 3, dtype=np.float32)
+        # the caller's accumulation buffer, page-locked as the contract asks (render_host copies pinned buffers
+        # directly and stages pageable ones)
+        host_t = torch.zeros(WIDTH * HEIGHT * 3, dtype=torch.float32).pin_memory()
+        host = host_t.numpy()
         r.set_stream(None)
         with api.Renderer(profile=api.PROFILE_V2, math_mode=math_mode, num_bounces=BOUNCES, device=local_rank) as rh:
             rh.render_host(host, WIDTH, HEIGHT, NTX, NTY, 8)  # warm-up: allocations, pinned staging
             e2e_steps = max(1, min(args.steps, 3))
-            t0 = time.perf_counter()
+            sec = 0.0
             for _ in range(e2e_steps):
-                host[:] = 0.0
+                host[:] = 0.0  # a fresh accumulation state (not part of the call)
                 rh.frame_counter = 0
-                rh.render_host(host, WIDTH, HEIGHT, NTX, NTY, spp)
+                t0 = time.perf_counter()
+                rh.render_host(host, WIDTH, HEIGHT, NTX, NTY, spp)  # H2D of the state, render, D2H of the result
                 checksum = float(host[::4097].sum())  # device->host result is read on the host
-            sec = time.perf_counter() - t0
+                sec += time.perf_counter() - t0
         e2e = {"value": WIDTH * HEIGHT * spp * e2e_steps / sec * 1e-6, "unit": "Mpaths/s",
                "h2d_bytes_per_step": WIDTH * HEIGHT * 3 * 4, "d2h_bytes_per_step": WIDTH * HEIGHT * 3 * 4,
-               "steps": e2e_steps, "api": "b200pt_render_host (DemofoxRenderV2 signature + frame count), wall clock",
+               "steps": e2e_steps, "api": "b200pt_render_host (DemofoxRenderV2 signature + frame count) on a page-locked host buffer, wall clock",
                "checksum": checksum}
     else:
         # N>1: every rank's result tensor is read back to pinned host memory inside the step

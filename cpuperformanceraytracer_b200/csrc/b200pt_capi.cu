@@ -574,7 +574,20 @@ int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H
         }
     }
     const size_t nfloats = (size_t)W * H * 3;
-    if (c->pinned_floats != nfloats) {
+    // A caller buffer that is already page-locked (cudaHostAlloc / cudaHostRegister) is copied directly; pageable
+    // memory (the reference's _aligned_malloc) goes through the context's pinned staging buffers.
+    auto is_pinned = [](const void* ptr) {
+        cudaPointerAttributes a{};
+        if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) {
+            cudaGetLastError();
+            return false;
+        }
+        return a.type == cudaMemoryTypeHost;
+    };
+    const bool direct = is_pinned(BufferOut);
+    const bool want_screen = ScreenBufferData && c->params.output_to_screen;
+    const bool direct_screen = want_screen && is_pinned(ScreenBufferData);
+    if ((!direct || (want_screen && !direct_screen)) && c->pinned_floats != nfloats) {
         if (c->h_pinned) cudaFreeHost(c->h_pinned);
         if (c->h_pinned_screen) cudaFreeHost(c->h_pinned_screen);
         c->h_pinned = nullptr;
@@ -583,19 +596,22 @@ int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H
         CUDA_TRY(c, cudaMallocHost(&c->h_pinned_screen, (size_t)W * H * sizeof(uint32_t)));
         c->pinned_floats = nfloats;
     }
-    // host accumulation state -> pinned staging -> HBM; render; HBM -> pinned -> host
-    std::memcpy(c->h_pinned, BufferOut, nfloats * sizeof(float));
-    CUDA_TRY(c, cudaMemcpyAsync(c->d_target, c->h_pinned, nfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    // host accumulation state -> (pinned staging ->) HBM; render; HBM -> (pinned ->) host
+    float* src = BufferOut;
+    if (!direct) {
+        std::memcpy(c->h_pinned, BufferOut, nfloats * sizeof(float));
+        src = c->h_pinned;
+    }
+    CUDA_TRY(c, cudaMemcpyAsync(c->d_target, src, nfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     int rc = b200pt_render_frames(c, nframes);
     if (rc != B200PT_OK) return rc;
-    CUDA_TRY(c, cudaMemcpyAsync(c->h_pinned, c->d_target, nfloats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
-    const bool want_screen = ScreenBufferData && c->params.output_to_screen;
+    CUDA_TRY(c, cudaMemcpyAsync(src, c->d_target, nfloats * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
     if (want_screen)
-        CUDA_TRY(c, cudaMemcpyAsync(c->h_pinned_screen, c->d_screen, (size_t)W * H * sizeof(uint32_t),
-                                    cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(c, cudaMemcpyAsync(direct_screen ? ScreenBufferData : (void*)c->h_pinned_screen, c->d_screen,
+                                    (size_t)W * H * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    std::memcpy(BufferOut, c->h_pinned, nfloats * sizeof(float));
-    if (want_screen) std::memcpy(ScreenBufferData, c->h_pinned_screen, (size_t)W * H * sizeof(uint32_t));
+    if (!direct) std::memcpy(BufferOut, c->h_pinned, nfloats * sizeof(float));
+    if (want_screen && !direct_screen) std::memcpy(ScreenBufferData, c->h_pinned_screen, (size_t)W * H * sizeof(uint32_t));
     return collect_timing(c);
 }
 
