@@ -477,6 +477,7 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     rp.group_offset = (c->num_tiles > 0 ? c->first_tile : 0) * rp.groups_per_tile;
     rp.num_groups = ntiles * rp.groups_per_tile;
     rp.num_items = (rp.num_groups + 3) / 4;
+    rp.block_items = (c->tile_h % 4 == 0) ? 1 : 0;
     rp.first_frame = c->iframe + 1;  // iFrame += 1 before the render, v4.cpp:1703
     rp.nframes = nframes;
     rp.num_bounces = c->params.num_bounces;

@@ -145,6 +145,7 @@ struct RenderParams {
     int num_groups;           // SoA8 groups rendered by this launch (whole image, or a band of tile rows)
     int group_offset;         // first group of the band (tile-shard: a rank's tile rows are contiguous)
     int num_items;            // ceil(num_groups / 4): one warp = 4 groups = 32 pixels
+    int block_items;          // tile_h % 4 == 0: an item is an 8x4 pixel block (4 groups stacked in y) instead of a 32x1 strip
     int first_frame;          // 1-based iFrame of the first render call in this launch
     int nframes;
     int num_bounces;
