@@ -172,11 +172,34 @@ def run_reference_arm(args):
         "e2e": {"value": base["value"], "unit": "Mpaths/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
+_JSON_FD = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: whatever libraries print there (NCCL's version banner, ...) is sent to
+    stderr by pointing fd 1 at fd 2; the JSON line goes to the saved original descriptor."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -364,7 +387,7 @@ def main():
         }
         if cpu_base is not None:
             line["cpu_baseline"] = cpu_base
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         tdist.barrier()
         tdist.destroy_process_group()
