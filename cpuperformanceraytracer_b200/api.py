@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
     "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
-    "b200pt_eval_portable", "b200pt_check_portable_tiers",
+    "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match",
 ]
 FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP, FN_SQRT, FN_RCP, FN_DIV, FN_EQUIRECT_TEXEL = 0, 1, 2, 3, 4, 5, 6, 7, 8
 

@@ -116,15 +116,10 @@ LaunchConfig launch_config(const b200pt_context* c)
     lc.accum_mode = c->params.accum_mode;
     lc.static_scene = (c->params.generic_scene_tables || c->custom_scene) ? 0 : 1;
     if (lc.profile == kProfileV4 && lc.static_scene && !v4_scene_matches_static_tables(c->scenes.v4)) lc.static_scene = 0;
-    if (lc.static_scene && lc.profile != kProfileV4) {  // the legacy kernels' immediate sphere data must be what the host built
-        const bool v3r = lc.profile == kProfileV3Redo;
-        for (int i = 0; i < (v3r ? kV3Spheres : kCornellSpheres); i++) {
-            const float4 S = v3r ? c->scenes.v3redo.sphere[i] : c->scenes.cornell.sphere[i];
-            const bool same = v3r ? (S.x == v4_sphere_x(i) && S.y == kV4SphereY && S.z == kV4SphereZ && S.w == kV4SphereRadius)
-                                  : (S.x == cornell_sphere_x(i) && S.y == kCornellSphereY && S.z == kCornellSphereZ && S.w == kCornellSphereRadius);
-            if (!same) lc.static_scene = 0;
-        }
-    }
+    if (lc.static_scene && lc.profile == kProfileV3Redo && !v3redo_spheres_match_static_tables(c->scenes.v3redo.sphere)) lc.static_scene = 0;
+    if (lc.static_scene && (lc.profile == kProfileV2 || lc.profile == kProfileSimtTextured) &&
+        !cornell_spheres_match_static_tables(c->scenes.cornell.sphere))
+        lc.static_scene = 0;
     lc.block = 256;
     lc.grid = 1;
     return lc;
@@ -787,6 +782,29 @@ int b200pt_check_portable_tiers(b200pt_context* c, int fn, uint64_t first, uint6
     *mismatches = h[0];
     if (literal_path) *literal_path = h[1];
     return B200PT_OK;
+}
+
+int b200pt_static_tables_match(int profile)
+{
+    switch (profile) {
+    case B200PT_PROFILE_V2:
+    case B200PT_PROFILE_SIMT_TEXTURED: {
+        CornellScene s;
+        build_cornell_scene(&s, profile == B200PT_PROFILE_SIMT_TEXTURED);
+        return cornell_spheres_match_static_tables(s.sphere) ? 1 : 0;
+    }
+    case B200PT_PROFILE_OPT_V4: {
+        V4Scene s;
+        build_v4_scene(&s);
+        return v4_scene_matches_static_tables(s) ? 1 : 0;
+    }
+    case B200PT_PROFILE_V3_REDO: {
+        V3RedoScene s;
+        build_v3redo_scene(&s);
+        return v3redo_spheres_match_static_tables(s.sphere) ? 1 : 0;
+    }
+    default: return -1;
+    }
 }
 
 int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float* rects, int32_t* count)

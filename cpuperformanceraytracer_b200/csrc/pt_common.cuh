@@ -100,6 +100,23 @@ inline bool v4_scene_matches_static_tables(const V4Scene& s)
     return true;
 }
 
+// the legacy kernels' immediate sphere data (Cornell: v2 / simt_textured) against a host-built scene
+inline bool cornell_spheres_match_static_tables(const float4* sphere)
+{
+    for (int i = 0; i < 3; i++)
+        if (sphere[i].x != cornell_sphere_x(i) || sphere[i].y != kCornellSphereY || sphere[i].z != kCornellSphereZ ||
+            sphere[i].w != kCornellSphereRadius)
+            return false;
+    return true;
+}
+inline bool v3redo_spheres_match_static_tables(const float4* sphere)
+{
+    for (int i = 0; i < kV4Spheres; i++)
+        if (sphere[i].x != v4_sphere_x(i) || sphere[i].y != kV4SphereY || sphere[i].z != kV4SphereZ || sphere[i].w != kV4SphereRadius)
+            return false;
+    return true;
+}
+
 // Scene of demofox_path_tracing_v3_redo.cpp, SCENE 1 (:485-600): the v4 geometry tested with the
 // legacy (ScalarTriple) quad test, exact-arithmetic Fresnel materials, a striped backdrop whose
 // albedo is computed at the hit (:511-515), GetZeroedMaterial IOR = 1 for the quads (:155-168).

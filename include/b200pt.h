@@ -232,6 +232,11 @@ int b200pt_eval_portable(b200pt_context* ctx, int fn, const float* a, const floa
 int b200pt_check_portable_tiers(b200pt_context* ctx, int fn, uint64_t first, uint64_t count, uint64_t* mismatches,
                                 uint64_t* literal_path);
 
+/* Host-only check (no GPU needed): 1 when the built-in scene of `profile`, as the host builds it, agrees with the
+ * compile-time tables the scene-specialised kernels assume (sphere centres / radii as immediates, zero components of
+ * the v4 quad tables); 0 = the library would fall back to the generic kernels; -1 = unknown profile. */
+int b200pt_static_tables_match(int profile);
+
 /* Host-only helper (no GPU needed): the conservative fragCoord-space rectangles (x0, y0, x1, y1;
  * y = flipped row index) outside of which a camera ray of `profile` cannot hit the scene; the kernel
  * skips the scene trace for such pixels.  rects must hold 4 * 12 floats; *count < 0 = no culling. */

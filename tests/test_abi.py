@@ -30,6 +30,16 @@ def test_header_symbols_exported():
     assert lib.b200pt_api_version() == 1
 
 
+def test_built_in_scenes_match_the_specialised_kernels_tables():
+    """the scene-specialised kernels' compile-time tables (sphere data as immediates, zero components of the v4 quad
+    vectors) are what the host builds from the reference's scene expressions -- otherwise the library would silently
+    run the slower generic kernels"""
+    lib = api.load_library()
+    for profile in (api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_OPT_V4, api.PROFILE_V3_REDO):
+        assert lib.b200pt_static_tables_match(profile) == 1
+    assert lib.b200pt_static_tables_match(99) == -1
+
+
 def test_default_params_follow_reference_flags():
     p = api.default_params(api.PROFILE_OPT_V4)  # global_preprocessor_flags.h:56-66
     assert (p.env_kind, p.env_sampler, p.accum_mode, p.math_mode) == (api.ENV_EQUIRECT, api.SAMPLER_RANDOM,
