@@ -174,7 +174,8 @@ __device__ __forceinline__ bool rounds_safely(double d)
     return (dropped - (0x10000000u - 1024u)) > 2048u && hi >= 0x38700000u;  // |d| >= 2^-120
 }
 
-__device__ __forceinline__ float atan2f_portable(float yf, float xf)
+// first tier: true and the result when it is decisive
+__device__ __forceinline__ bool atan2f_first_tier(float yf, float xf, float& out)
 {
     const double PI = 3.14159265358979311600e+00, PIO2 = 1.57079632679489655800e+00;
     const double x = (double)xf, y = (double)yf;
@@ -207,12 +208,24 @@ __device__ __forceinline__ float atan2f_portable(float yf, float xf)
         double r = __dmul_rn(t, p);
         if (steep) r = __dsub_rn(PIO2, r);
         if (__float_as_int(xf) < 0) r = __dsub_rn(PI, r);  // signbit(x), -0 included
-        if (rounds_safely(r)) return copysignf(__double2float_rn(r), yf);
+        if (rounds_safely(r)) {
+            out = copysignf(__double2float_rn(r), yf);
+            return true;
+        }
     }
+    return false;
+}
+__device__ __forceinline__ float atan2f_portable(float yf, float xf)
+{
+    float r;
+    if (atan2f_first_tier(yf, xf, r)) return r;
+    // NaN directions are not rare (v3_redo / v4: total internal reflection in the roughness-0 sphere yields a zero
+    // vector, normalised to NaN, exactly as in the reference): the literal algorithm's answer is the quiet NaN
+    if (yf != yf || xf != xf) return __int_as_float(0x7fc00000);
     return atan2f_literal(yf, xf);
 }
 
-__device__ __forceinline__ float asinf_portable(float v)
+__device__ __forceinline__ bool asinf_first_tier(float v, float& out)
 {
     const double PIO2 = 1.57079632679489655800e+00;
     const double ax = fabs((double)v);
@@ -238,8 +251,18 @@ __device__ __forceinline__ float asinf_portable(float v)
         p = __fma_rn(u, p, c_asin[0]);
         double r = __fma_rn(__dmul_rn(t, u), p, t);  // asin(t) = t + t^3 P(t^2)
         if (big) r = __fma_rn(r, -2.0, PIO2);
-        if (rounds_safely(r)) return copysignf(__double2float_rn(r), v);
+        if (rounds_safely(r)) {
+            out = copysignf(__double2float_rn(r), v);
+            return true;
+        }
     }
+    return false;
+}
+__device__ __forceinline__ float asinf_portable(float v)
+{
+    float r;
+    if (asinf_first_tier(v, r)) return r;
+    if (!(fabsf(v) <= 1.0f)) return __int_as_float(0x7fc00000);  // |v| > 1 or NaN: what the literal algorithm returns
     return asinf_literal(v);
 }
 
@@ -247,6 +270,7 @@ __device__ __forceinline__ float asinf_portable(float v)
 // Taylor polynomial, scaling through the exponent field, one rounding to binary32
 __device__ __forceinline__ float expf_portable(float a)
 {
+    if (a == 0.f) return 1.0f;  // what the evaluation below gives; the built-in refraction colour has a zero channel
     double x = (double)a;
     if (x != x) return __int_as_float(0x7fc00000);
     if (x > 89.0) return __int_as_float(0x7f800000);
