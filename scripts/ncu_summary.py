@@ -50,6 +50,14 @@ for ln in sass:
         chain.append((m.group(1).split('/')[-1], int(m.group(2))))
         cur = chain[0]
         continue
+    m = re.match(r'\s*(\$[\w$.]+):\s*$', ln)
+    if m:  # a subroutine embedded in the kernel (IEEE slow paths, noinline device functions): most carry no line info
+        name = m.group(1)
+        short = re.sub(r'^\$__internal_\d+_\$', '', name) if name.startswith('$__internal') else name.split('$')[-1][:60]
+        chain = [('<' + short + '>', 0)]
+        cur = chain[0]
+        fresh = True
+        continue
     m = re.match(r'\s*/\*([0-9a-f]{4,})\*/\s+(.*);', ln)
     if m:
         off2[int(m.group(1), 16)] = (cur, m.group(2).strip()); offchain[int(m.group(1), 16)] = tuple(chain); fresh = True
@@ -65,7 +73,7 @@ for r in rows[2:]:
     key = cur if cur else ('?', 0)
     inst, th, sm = int(r[ii]), int(r[it]), int(r[isamp])
     b = by[key]; b[0] += inst; b[1] += th; b[2] += sm
-    ch = [c for c in offchain.get(a - base, ()) if c[0].endswith('.cuh') or c[0].endswith('.cu')]
+    ch = [c for c in offchain.get(a - base, ()) if c[0].endswith('.cuh') or c[0].endswith('.cu') or c[0].startswith('<')]
     for lvl in range(3):
         k2 = tuple(reversed(ch[-(lvl + 1):])) if ch else (('?', 0),)
         b = bysite[lvl][k2]; b[0] += inst; b[1] += th; b[2] += sm
@@ -86,6 +94,6 @@ with open(outp + "_hotspots.txt", "w") as f:
     for lvl in range(3):
         f.write('\nby call site, %d frame(s) below the kernel body (root first)\n' % lvl)
         for key, b in sorted(bysite[lvl].items(), key=lambda kv: -kv[1][0])[:(20, 45, 70)[lvl]]:
-            f.write('%-34s inst%%=%5.2f eff=%5.1f samp%%=%5.2f | %s\n' % ('>'.join('%d' % k[1] for k in key), 100 * b[0] / tot[0], b[1] / max(b[0], 1),
+            f.write('%-34s inst%%=%5.2f eff=%5.1f samp%%=%5.2f | %s\n' % ('>'.join(('%d' % k[1]) if not k[0].startswith('<') else k[0] for k in key), 100 * b[0] / tot[0], b[1] / max(b[0], 1),
                                                                        100 * b[2] / max(tot[2], 1), srcline(*key[-1])))
 print(open(outp + "_hotspots.txt").read())
