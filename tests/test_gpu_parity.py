@@ -307,6 +307,26 @@ def test_full_size_bit_exact_vs_oracle(oracle):
     assert (c["paths"], c["segments"], c["escapes"]) == (oc["paths"], oc["segments"], oc["escapes"])
 
 
+@pytest.mark.parametrize("profile,W,H,ntx,nty,bounces,frames,envshape,ek,es", [
+    (0, 4096, 4096, 16, 32, 16, 2, None, 0, 0),          # BASELINE config 5 geometry class: 16 bounces, large square image
+    (2, 3840, 2160, 10, 15, 8, 2, (2048, 1024), 1, 2),   # config 3 geometry: 4K, v4, 2048x1024 equirect, random-jitter sampler
+    (1, 3840, 2160, 10, 15, 8, 1, (2048, 1024), 1, 0),   # config 3: simt_textured, point sampler
+], ids=["v2_4096sq_16b", "v4_4k_equirect", "simt_4k"])
+def test_large_images_bit_exact_vs_oracle(oracle, profile, W, H, ntx, nty, bounces, frames, envshape, ek, es):
+    """the BASELINE configurations' image sizes at a bounded frame count: whole buffers and counters equal the oracle's"""
+    env = oracle.synthetic_env(*envshape) if envshape else None
+    o, oc = oracle.render(profile, W, H, ntx, nty, bounces, frames, env=env, env_kind=ek, env_sampler=es)
+    with make_renderer(profile, bounces, ek, es) as r:
+        if env is not None:
+            r.set_env(env)
+        r.resize(W, H, ntx, nty)
+        r.render_frames(frames)
+        g = r.download_target()
+        c = r.counters()
+    assert np.array_equal(g, o)
+    assert (c["paths"], c["segments"], c["escapes"]) == (oc["paths"], oc["segments"], oc["escapes"])
+
+
 def test_randomised_configurations_bit_exact(oracle):
     """Seeded sweep over resolution, tiling, bounce budget, frame offset, profile and a random
     pre-existing accumulation state: GPU == oracle, bit for bit."""
