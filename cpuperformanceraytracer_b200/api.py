@@ -244,8 +244,12 @@ class Renderer:
         self._check(rc, "b200pt_render_host")
         self.width, self.height, self.ntx, self.nty = width, height, ntx, nty
 
-    def resolve_ldr(self, mode=LDR_FILE_RGBA, bump_frame_counter=False):
-        out = np.empty((self.height, self.width), dtype=np.uint32)
+    def resolve_ldr(self, mode=LDR_FILE_RGBA, bump_frame_counter=False, out=None):
+        """tone-mapped u32 frame; `out` = a caller-owned (H, W) uint32 array to fill (page-locked memory is copied
+        into directly at PCIe speed), default a fresh array"""
+        if out is None:
+            out = np.empty((self.height, self.width), dtype=np.uint32)
+        assert out.dtype == np.uint32 and out.flags["C_CONTIGUOUS"] and out.size == self.height * self.width
         rc = self._lib.b200pt_resolve_ldr(self._ctx, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), mode,
                                           int(bump_frame_counter))
         self._check(rc, "b200pt_resolve_ldr")
