@@ -28,8 +28,14 @@ ABI_SYMBOLS = [
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
     "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
-    "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match",
+    "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_scale_target",
+    "b200pt_group_create", "b200pt_group_destroy", "b200pt_group_size", "b200pt_group_context", "b200pt_group_set_env",
+    "b200pt_group_resize", "b200pt_group_reset", "b200pt_group_set_frame_counter", "b200pt_group_get_frame_counter",
+    "b200pt_group_render_frames", "b200pt_group_synchronize", "b200pt_group_upload_target", "b200pt_group_download_target",
+    "b200pt_group_render_host", "b200pt_group_resolve_ldr", "b200pt_group_get_counters", "b200pt_group_last_error",
 ]
+SHARD_SPP, SHARD_TILES = 0, 1
+COMBINE_NCCL, COMBINE_PEER = 0, 1
 FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP, FN_SQRT, FN_RCP, FN_DIV, FN_EQUIRECT_TEXEL = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 
@@ -49,7 +55,7 @@ class Params(ctypes.Structure):
 
 class Counters(ctypes.Structure):
     _fields_ = [("paths", ctypes.c_uint64), ("segments", ctypes.c_uint64), ("escapes", ctypes.c_uint64),
-                ("launches", ctypes.c_uint64), ("last_render_ms", ctypes.c_double)]
+                ("launches", ctypes.c_uint64), ("last_render_ms", ctypes.c_double), ("culled_segments", ctypes.c_uint64)]
 
 
 class B200PTError(RuntimeError):
@@ -104,6 +110,27 @@ def load_library():
     L.b200pt_check_portable_tiers.argtypes = [vp, ctypes.c_int, ctypes.c_uint64, ctypes.c_uint64, ctypes.POINTER(ctypes.c_uint64),
                                               ctypes.POINTER(ctypes.c_uint64)]
     L.b200pt_compute_cull_rects.argtypes = [ctypes.c_int, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
+    L.b200pt_scale_target.argtypes = [vp, ctypes.c_float]
+    # several GPUs of one process
+    L.b200pt_group_create.argtypes = [ctypes.POINTER(Params), ctypes.POINTER(i32), i32, i32, i32, ctypes.POINTER(vp)]
+    L.b200pt_group_destroy.argtypes = [vp]
+    L.b200pt_group_size.argtypes = [vp]
+    L.b200pt_group_context.argtypes = [vp, i32]
+    L.b200pt_group_context.restype = vp
+    L.b200pt_group_set_env.argtypes = [vp, Texture]
+    L.b200pt_group_resize.argtypes = [vp, i32, i32, i32, i32]
+    L.b200pt_group_reset.argtypes = [vp]
+    L.b200pt_group_set_frame_counter.argtypes = [vp, i32]
+    L.b200pt_group_get_frame_counter.argtypes = [vp, ctypes.POINTER(i32)]
+    L.b200pt_group_render_frames.argtypes = [vp, i32]
+    L.b200pt_group_synchronize.argtypes = [vp]
+    L.b200pt_group_upload_target.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.b200pt_group_download_target.argtypes = [vp, ctypes.POINTER(ctypes.c_float)]
+    L.b200pt_group_render_host.argtypes = [vp, ctypes.POINTER(ctypes.c_float), i32, i32, i32, i32, i32, i32, i32, Texture, vp, i32]
+    L.b200pt_group_resolve_ldr.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32), i32, i32]
+    L.b200pt_group_get_counters.argtypes = [vp, ctypes.POINTER(Counters), ctypes.POINTER(ctypes.c_double)]
+    L.b200pt_group_last_error.argtypes = [vp]
+    L.b200pt_group_last_error.restype = ctypes.c_char_p
     _lib = L
     return L
 
@@ -294,7 +321,7 @@ class Renderer:
         c = Counters()
         self._check(self._lib.b200pt_get_counters(self._ctx, ctypes.byref(c)), "b200pt_get_counters")
         return {"paths": c.paths, "segments": c.segments, "escapes": c.escapes, "launches": c.launches,
-                "last_render_ms": c.last_render_ms}
+                "last_render_ms": c.last_render_ms, "culled_segments": c.culled_segments}
 
     # -- multi-GPU plumbing ------------------------------------------------------------------------
     def bind_device_target(self, device_ptr):
@@ -317,6 +344,124 @@ class Renderer:
 
     def finalize_sum(self, total_frames):
         self._check(self._lib.b200pt_finalize_sum(self._ctx, int(total_frames)), "b200pt_finalize_sum")
+
+    def scale_target(self, factor):
+        self._check(self._lib.b200pt_scale_target(self._ctx, ctypes.c_float(factor)), "b200pt_scale_target")
+
+
+class Group:
+    """Several GPUs of this process behind one set of render entry points (b200pt_group_*): frames (SHARD_SPP) or
+    tiles (SHARD_TILES) of every render call are sharded over `devices`; the image lives on devices[0]."""
+
+    def __init__(self, devices, sharding=SHARD_SPP, combine=COMBINE_NCCL, profile=PROFILE_V2, math_mode=MATH_PARITY,
+                 num_bounces=-1, env_kind=None, env_sampler=None, output_to_screen=False):
+        self._lib = load_library()
+        self._g = ctypes.c_void_p()
+        p = default_params(profile)
+        p.math_mode, p.num_bounces = math_mode, num_bounces
+        p.output_to_screen = int(bool(output_to_screen))
+        if env_kind is not None:
+            p.env_kind = env_kind
+        if env_sampler is not None:
+            p.env_sampler = env_sampler
+        devs = (ctypes.c_int32 * len(devices))(*devices)
+        rc = self._lib.b200pt_group_create(ctypes.byref(p), devs, len(devices), sharding, combine, ctypes.byref(self._g))
+        if rc != 0:
+            self._g = ctypes.c_void_p()
+            raise B200PTError(f"b200pt_group_create failed: {self._lib.b200pt_error_string(rc).decode()} "
+                              "(B200s are required; there is no CPU fallback)")
+        self.size = len(devices)
+        self.width = self.height = self.ntx = self.nty = 0
+        self._env_keep = None
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise B200PTError(f"{what}: {self._lib.b200pt_error_string(rc).decode()}: "
+                              f"{self._lib.b200pt_group_last_error(self._g).decode()}")
+
+    def close(self):
+        if self._g:
+            self._lib.b200pt_group_destroy(self._g)
+            self._g = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_env(self, env):
+        e = np.ascontiguousarray(env, dtype=np.float32)
+        self._env_keep = e
+        self._check(self._lib.b200pt_group_set_env(self._g, Texture(_fptr(e), e.shape[1], e.shape[0], 3)), "b200pt_group_set_env")
+
+    def resize(self, width, height, ntx, nty):
+        self._check(self._lib.b200pt_group_resize(self._g, width, height, ntx, nty), "b200pt_group_resize")
+        self.width, self.height, self.ntx, self.nty = width, height, ntx, nty
+
+    def reset(self):
+        self._check(self._lib.b200pt_group_reset(self._g), "b200pt_group_reset")
+
+    @property
+    def frame_counter(self):
+        v = ctypes.c_int32()
+        self._check(self._lib.b200pt_group_get_frame_counter(self._g, ctypes.byref(v)), "b200pt_group_get_frame_counter")
+        return v.value
+
+    @frame_counter.setter
+    def frame_counter(self, v):
+        self._check(self._lib.b200pt_group_set_frame_counter(self._g, int(v)), "b200pt_group_set_frame_counter")
+
+    def render_frames(self, nframes, sync=True):
+        self._check(self._lib.b200pt_group_render_frames(self._g, int(nframes)), "b200pt_group_render_frames")
+        if sync:
+            self.synchronize()
+
+    def synchronize(self):
+        self._check(self._lib.b200pt_group_synchronize(self._g), "b200pt_group_synchronize")
+
+    def upload_target(self, buf):
+        b = np.ascontiguousarray(buf, dtype=np.float32).reshape(-1)
+        assert b.size == self.width * self.height * 3
+        self._check(self._lib.b200pt_group_upload_target(self._g, _fptr(b)), "b200pt_group_upload_target")
+
+    def download_target(self):
+        out = np.empty(self.width * self.height * 3, dtype=np.float32)
+        self._check(self._lib.b200pt_group_download_target(self._g, _fptr(out)), "b200pt_group_download_target")
+        return out
+
+    def render_host(self, buffer_out, width, height, ntx, nty, nframes, env=None, screen=None):
+        assert buffer_out.dtype == np.float32 and buffer_out.flags["C_CONTIGUOUS"]
+        if env is not None:
+            e = env if (env.dtype == np.float32 and env.flags["C_CONTIGUOUS"]) else np.ascontiguousarray(env, np.float32)
+            self._env_keep = e
+            t = Texture(_fptr(e), e.shape[1], e.shape[0], 3)
+        else:
+            t = Texture(None, 0, 0, 3)
+        sp = screen.ctypes.data_as(ctypes.c_void_p) if screen is not None else None
+        rc = self._lib.b200pt_group_render_host(self._g, _fptr(buffer_out), width, height, ntx, nty, width // ntx,
+                                                height // nty, 3, t, sp, int(nframes))
+        self._check(rc, "b200pt_group_render_host")
+        self.width, self.height, self.ntx, self.nty = width, height, ntx, nty
+
+    def resolve_ldr(self, mode=LDR_FILE_RGBA, bump_frame_counter=False):
+        out = np.empty((self.height, self.width), dtype=np.uint32)
+        rc = self._lib.b200pt_group_resolve_ldr(self._g, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), mode,
+                                                int(bump_frame_counter))
+        self._check(rc, "b200pt_group_resolve_ldr")
+        return out
+
+    def counters(self):
+        c, ms = Counters(), ctypes.c_double()
+        self._check(self._lib.b200pt_group_get_counters(self._g, ctypes.byref(c), ctypes.byref(ms)), "b200pt_group_get_counters")
+        return {"paths": c.paths, "segments": c.segments, "escapes": c.escapes, "launches": c.launches,
+                "last_render_ms": c.last_render_ms, "culled_segments": c.culled_segments, "combine_ms": ms.value}
 
 
 def cull_rects(profile, width, height):

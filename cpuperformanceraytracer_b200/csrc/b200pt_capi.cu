@@ -2,100 +2,13 @@
 // Owns the device state the reference keeps in file-scope statics (frame counter, scene, tile
 // table: demofox_path_tracing_optimization_v4.cpp:34,378,386,1343) plus the HBM copies of the
 // caller's buffers.  No CPU rendering path exists here: without a usable GPU every call fails.
-#include "../../include/b200pt.h"
-
 #include <cstdio>
 #include <cstring>
 #include <new>
-#include <string>
-#include <vector>
 
-#include "../host/scene_setup.h"
-#include "pt_common.cuh"
-
-using namespace b200pt;
-
-struct b200pt_context {
-    b200pt_params params{};
-    int device = 0;
-    int sm_count = 0;
-    cudaStream_t own_stream = nullptr;
-    cudaStream_t stream = nullptr;  // own_stream or a caller-provided one
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-
-    SceneSet scenes{};
-    bool custom_scene = false;            // b200pt_set_scene_v4 installed a scene
-    std::vector<float> scene_quads, scene_spheres;  // host copies for the culling rectangles
-    float scene_cam[4] = {0.f, 0.f, 40.f, 1.f};
-    float cameraDistance = 1.f;
-
-    // target
-    int width = 0, height = 0, ntx = 0, nty = 0, tile_w = 0, tile_h = 0;
-    float* d_target_own = nullptr;
-    float* d_target = nullptr;  // own or bound
-    uint32_t* d_screen = nullptr;       // slot 0 of the present ring; also used by resolve_ldr / render_host
-    uint32_t* d_screen1 = nullptr;      // slot 1
-    uint32_t* h_ring[2] = {nullptr, nullptr};  // pinned host frames of the present ring
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t render_done[2] = {nullptr, nullptr}, copy_done[2] = {nullptr, nullptr};
-    int ring_frame[2] = {0, 0};
-    unsigned long long submitted = 0, acquired = 0;
-    uint32_t* d_rng = nullptr;
-    int* d_work_counter = nullptr;
-    DeviceCounters* d_counters = nullptr;
-    float* h_pinned = nullptr;  // staging for render_host (pinned, W*H*3 floats)
-    uint32_t* h_pinned_screen = nullptr;
-    size_t pinned_floats = 0;
-
-    // env
-    float* d_env_rgb = nullptr;
-    float4* d_env_rgba = nullptr;
-    cudaTextureObject_t env_tex = 0;
-    int env_w = 0, env_h = 0;
-    const float* last_env_ptr = nullptr;
-
-    int iframe = 0;
-    int first_tile = 0, num_tiles = 0;  // flat tile range rendered by this context (0, 0 = all tiles)
-    int blocks_per_sm = 0;
-    uint64_t paths = 0, launches = 0;
-    double last_render_ms = 0.0;
-    bool timing_pending = false;
-    std::string last_error;
-};
+#include "b200pt_context.h"
 
 namespace {
-
-// Every entry point works on the context's device but leaves the caller's current device untouched
-// (a host application -- or torch in the multi-GPU driver -- owns that setting).
-struct DeviceGuard {
-    int prev = -1;
-    cudaError_t status = cudaSuccess;
-    explicit DeviceGuard(int device)
-    {
-        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
-        status = (prev == device) ? cudaSuccess : cudaSetDevice(device);
-    }
-    ~DeviceGuard()
-    {
-        int cur = -1;
-        if (prev >= 0 && cudaGetDevice(&cur) == cudaSuccess && cur != prev) cudaSetDevice(prev);
-    }
-};
-
-int fail(b200pt_context* ctx, int code, const std::string& msg)
-{
-    if (ctx) ctx->last_error = msg;
-    return code;
-}
-
-#define CUDA_TRY(ctx, expr)                                                                         \
-    do {                                                                                            \
-        cudaError_t e_ = (expr);                                                                    \
-        if (e_ != cudaSuccess) {                                                                    \
-            return fail(ctx, e_ == cudaErrorMemoryAllocation ? B200PT_ERR_OUT_OF_MEMORY : B200PT_ERR_CUDA, \
-                        std::string(#expr) + ": " + cudaGetErrorString(e_));                        \
-        }                                                                                           \
-    } while (0)
 
 bool uses_env(const b200pt_params& p)
 {
@@ -127,14 +40,15 @@ LaunchConfig launch_config(const b200pt_context* c)
 
 void free_target(b200pt_context* c)
 {
+    if (c->copy_stream) cudaStreamSynchronize(c->copy_stream);  // a present copy may still read a ring slot
     if (c->d_target_own) cudaFree(c->d_target_own);
     if (c->d_screen) cudaFree(c->d_screen);
-    if (c->d_screen1) cudaFree(c->d_screen1);
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kRingSlots; i++) {
+        if (i > 0 && c->d_ring[i]) cudaFree(c->d_ring[i]);  // d_ring[0] is d_screen
+        c->d_ring[i] = nullptr;
         if (c->h_ring[i]) cudaFreeHost(c->h_ring[i]);
         c->h_ring[i] = nullptr;
     }
-    c->d_screen1 = nullptr;
     c->submitted = c->acquired = 0;
     if (c->d_rng) cudaFree(c->d_rng);
     if (c->h_pinned) cudaFreeHost(c->h_pinned);
@@ -159,14 +73,26 @@ void free_env(b200pt_context* c)
     c->last_env_ptr = nullptr;
 }
 
-int collect_timing(b200pt_context* c)
+// Device time of render launches, CUDA events on the launching stream.  wait = false (the launch path): only
+// launches that have already finished are harvested -- the host is never blocked behind an earlier kernel, so
+// callers can queue ahead.  wait = true (synchronize / download / get_counters): everything pending is
+// collected; the newest launch wins.
+int collect_timing(b200pt_context* c, bool wait)
 {
-    if (c->timing_pending) {
+    for (unsigned k = 0; k < 2; k++) {
+        const unsigned slot = (c->timing_slot + k) & 1u;  // older pair first
+        if (!c->timing_pending[slot]) continue;
+        if (!wait) {
+            const cudaError_t q = cudaEventQuery(c->ev1[slot]);
+            if (q == cudaErrorNotReady) continue;
+            CUDA_TRY(c, q);
+        } else {
+            CUDA_TRY(c, cudaEventSynchronize(c->ev1[slot]));
+        }
         float ms = 0.f;
-        CUDA_TRY(c, cudaEventSynchronize(c->ev1));
-        CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        CUDA_TRY(c, cudaEventElapsedTime(&ms, c->ev0[slot], c->ev1[slot]));
         c->last_render_ms = ms;
-        c->timing_pending = false;
+        c->timing_pending[slot] = false;
     }
     return B200PT_OK;
 }
@@ -253,9 +179,12 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
         cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->render_done[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->render_done[1], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->render_done[2], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->copy_done[0], cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->copy_done[1], cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->copy_done[2], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreate(&c->ev0[0]) != cudaSuccess || cudaEventCreate(&c->ev1[0]) != cudaSuccess ||
+        cudaEventCreate(&c->ev0[1]) != cudaSuccess || cudaEventCreate(&c->ev1[1]) != cudaSuccess ||
         cudaMalloc(&c->d_work_counter, sizeof(int)) != cudaSuccess ||
         cudaMalloc(&c->d_counters, sizeof(DeviceCounters)) != cudaSuccess ||
         cudaMemset(c->d_counters, 0, sizeof(DeviceCounters)) != cudaSuccess) {
@@ -292,12 +221,14 @@ int b200pt_destroy(b200pt_context* c)
     if (c->d_work_counter) cudaFree(c->d_work_counter);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < kRingSlots; i++) {
         if (c->render_done[i]) cudaEventDestroy(c->render_done[i]);
         if (c->copy_done[i]) cudaEventDestroy(c->copy_done[i]);
     }
-    if (c->ev0) cudaEventDestroy(c->ev0);
-    if (c->ev1) cudaEventDestroy(c->ev1);
+    for (int i = 0; i < 2; i++) {
+        if (c->ev0[i]) cudaEventDestroy(c->ev0[i]);
+        if (c->ev1[i]) cudaEventDestroy(c->ev1[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
     return B200PT_OK;
@@ -385,11 +316,21 @@ int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx,
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     const size_t nfloats = (size_t)width * height * 3;
     const bool bound = c->d_target && c->d_target != c->d_target_own;
-    if ((size_t)c->width * c->height != (size_t)width * height || !c->d_target_own) {
+    const bool realloc = (size_t)c->width * c->height != (size_t)width * height || !c->d_target_own;
+    // a caller-bound device target (b200pt_bind_device_target) was sized for the old image: refuse instead of
+    // silently rendering somewhere else than the buffer the caller keeps reducing
+    if (bound && realloc)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "a device target of another size is bound: b200pt_bind_device_target(ctx, NULL) first");
+    if (realloc) {
         free_target(c);
-        CUDA_TRY(c, cudaMalloc(&c->d_target_own, nfloats * sizeof(float)));
-        CUDA_TRY(c, cudaMalloc(&c->d_screen, (size_t)width * height * sizeof(uint32_t)));
-        CUDA_TRY(c, cudaMalloc(&c->d_rng, (size_t)width * height * sizeof(uint32_t)));
+        c->width = c->height = 0;  // a failed allocation leaves a consistent "not ready" context
+        cudaError_t e = cudaMalloc(&c->d_target_own, nfloats * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_screen, (size_t)width * height * sizeof(uint32_t));
+        if (e == cudaSuccess) e = cudaMalloc(&c->d_rng, (size_t)width * height * sizeof(uint32_t));
+        if (e != cudaSuccess) {
+            free_target(c);
+            CUDA_TRY(c, e);
+        }
         c->d_target = c->d_target_own;
     } else if (!bound) {
         c->d_target = c->d_target_own;
@@ -401,6 +342,9 @@ int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx,
     c->tile_w = width / ntx;
     c->tile_h = height / nty;
     c->first_tile = c->num_tiles = 0;
+    // frames still in the present ring belong to the old image
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
+    c->submitted = c->acquired = 0;
     return b200pt_reset(c);
 }
 
@@ -448,7 +392,7 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     if (nframes == 0) return B200PT_OK;
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
-    if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
+    if (collect_timing(c, false) != B200PT_OK) return B200PT_ERR_CUDA;  // poll only: never blocks the launch path
 
     RenderParams rp{};
     rp.target = c->d_target;
@@ -500,13 +444,15 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     if (lc.grid < 1) lc.grid = 1;
 
     CUDA_TRY(c, cudaMemsetAsync(c->d_work_counter, 0, sizeof(int), c->stream));
-    CUDA_TRY(c, cudaEventRecord(c->ev0, c->stream));
+    const unsigned ts = c->timing_slot;
+    c->timing_slot ^= 1u;
+    CUDA_TRY(c, cudaEventRecord(c->ev0[ts], c->stream));
     cudaError_t e = (c->params.math_mode == B200PT_MATH_PARITY)
                         ? launch_render_parity(lc, rp, c->scenes, c->stream)
                         : launch_render_fast(lc, rp, c->scenes, c->stream);
     CUDA_TRY(c, e);
-    CUDA_TRY(c, cudaEventRecord(c->ev1, c->stream));
-    c->timing_pending = true;
+    CUDA_TRY(c, cudaEventRecord(c->ev1[ts], c->stream));
+    c->timing_pending[ts] = true;
     c->launches++;
     c->iframe += nframes;
     c->paths += (uint64_t)rp.num_groups * 8u * (uint64_t)nframes;
@@ -520,7 +466,7 @@ int b200pt_synchronize(b200pt_context* c)
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return collect_timing(c);
+    return collect_timing(c, true);
 }
 
 int b200pt_upload_target(b200pt_context* c, const float* host_src)
@@ -544,7 +490,7 @@ int b200pt_download_target(b200pt_context* c, float* host_dst)
     CUDA_TRY(c, cudaMemcpyAsync(host_dst, c->d_target, (size_t)c->width * c->height * 3 * sizeof(float),
                                 cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    return collect_timing(c);
+    return collect_timing(c, true);
 }
 
 int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H, int32_t NumTilesX, int32_t NumTilesY,
@@ -608,7 +554,7 @@ int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
     if (!direct) std::memcpy(BufferOut, c->h_pinned, nfloats * sizeof(float));
     if (want_screen && !direct_screen) std::memcpy(ScreenBufferData, c->h_pinned_screen, (size_t)W * H * sizeof(uint32_t));
-    return collect_timing(c);
+    return collect_timing(c, true);
 }
 
 int b200pt_resolve_ldr(b200pt_context* c, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter)
@@ -639,11 +585,15 @@ int b200pt_present_submit(b200pt_context* c, int32_t nframes)
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     const size_t bytes = (size_t)c->width * c->height * sizeof(uint32_t);
-    if (!c->d_screen1) CUDA_TRY(c, cudaMalloc(&c->d_screen1, bytes));
-    for (int i = 0; i < 2; i++)
+    c->d_ring[0] = c->d_screen;
+    for (int i = 0; i < kRingSlots; i++) {
+        if (!c->d_ring[i]) CUDA_TRY(c, cudaMalloc(&c->d_ring[i], bytes));
         if (!c->h_ring[i]) CUDA_TRY(c, cudaMallocHost(&c->h_ring[i], bytes));
-    const int slot = (int)(c->submitted & 1ull);
-    uint32_t* dscreen = slot ? c->d_screen1 : c->d_screen;
+    }
+    // Slot k % 3.  Frame k's slot is written again by submit k + 3, which needs acquired >= k + 2, i.e. the caller
+    // has already asked for frame k + 1: the pointer handed out for frame k is dead by then (see b200pt.h).
+    const int slot = (int)(c->submitted % kRingSlots);
+    uint32_t* dscreen = c->d_ring[slot];
     const int rc = render_frames_impl(c, nframes, dscreen);
     if (rc != B200PT_OK) return rc;
     CUDA_TRY(c, cudaEventRecord(c->render_done[slot], c->stream));
@@ -661,7 +611,7 @@ int b200pt_present_acquire(b200pt_context* c, const uint32_t** frame, int32_t* i
     if (c->acquired >= c->submitted) return fail(c, B200PT_ERR_NOT_READY, "no frame in flight");
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
-    const int slot = (int)(c->acquired & 1ull);
+    const int slot = (int)(c->acquired % kRingSlots);
     CUDA_TRY(c, cudaEventSynchronize(c->copy_done[slot]));
     *frame = c->h_ring[slot];
     if (iframe) *iframe = c->ring_frame[slot];
@@ -692,7 +642,7 @@ int b200pt_set_stream(b200pt_context* c, void* cuda_stream)
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
+    if (collect_timing(c, true) != B200PT_OK) return B200PT_ERR_CUDA;
     c->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->own_stream;
     return B200PT_OK;
 }
@@ -727,6 +677,17 @@ int b200pt_finalize_sum(b200pt_context* c, int32_t total_frames)
     CUDA_TRY(c, guard.status);
     const float scale = 1.0f / ((float)total_frames + 1.f);
     CUDA_TRY(c, launch_scale(c->d_target, (size_t)c->width * c->height * 3, scale, c->stream));
+    c->launches++;
+    return B200PT_OK;
+}
+
+int b200pt_scale_target(b200pt_context* c, float factor)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
+    CUDA_TRY(c, launch_scale(c->d_target, (size_t)c->width * c->height * 3, factor, c->stream));
     c->launches++;
     return B200PT_OK;
 }
@@ -843,7 +804,7 @@ int b200pt_get_counters(b200pt_context* c, b200pt_counters* out)
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    if (collect_timing(c) != B200PT_OK) return B200PT_ERR_CUDA;
+    if (collect_timing(c, true) != B200PT_OK) return B200PT_ERR_CUDA;
     DeviceCounters dc{};
     CUDA_TRY(c, cudaMemcpy(&dc, c->d_counters, sizeof(dc), cudaMemcpyDeviceToHost));
     out->paths = c->paths;
@@ -851,6 +812,7 @@ int b200pt_get_counters(b200pt_context* c, b200pt_counters* out)
     out->escapes = dc.escapes;
     out->launches = c->launches;
     out->last_render_ms = c->last_render_ms;
+    out->culled_segments = dc.culled;
     return B200PT_OK;
 }
 

@@ -143,6 +143,7 @@ constexpr int kMaxCullRects = 12;
 struct DeviceCounters {
     unsigned long long segments;
     unsigned long long escapes;
+    unsigned long long culled;  // segments of camera-culled pixels: counted in `segments`, but no scene trace ran
 };
 
 // One launch = `nframes` consecutive render calls of the reference over the whole image.

@@ -53,10 +53,10 @@ def shard_tile_rows(width: int, height: int, num_tiles_y: int, world_size: int, 
     return TileRowShard(start, n, start * band, n * band)
 
 
-def finalize_scale(total_frames: int) -> float:
-    """1/(N+1): the reference's running average on a zeroed buffer is biased by design
-    (iFrame starts at 1 and the blend factor is 1/(iFrame+1))."""
-    return 1.0 / (float(total_frames) + 1.0)
+def finalize_scale(last_frame: int) -> float:
+    """1/(N+1) for a job whose last render call is frame N: the reference's running average on a zeroed buffer is
+    biased by design (iFrame starts at 1 and the blend factor is 1/(iFrame+1))."""
+    return 1.0 / (float(last_frame) + 1.0)
 
 
 def reduce_sum_(tensor, group=None):
@@ -87,15 +87,27 @@ class SppShardedRenderer:
         self.r.set_stream(self.stream.cuda_stream)
         torch.cuda.synchronize(self.device)
 
-    def render(self, total_frames, first_frame=1):
-        """Zeroes the buffer, renders this rank's frame block, reduces, scales.  Asynchronous."""
+    def render(self, total_frames, first_frame=1, resume=False):
+        """Renders frames [first_frame, first_frame + total_frames) of the job, sharded over the ranks, reduces, scales.
+        Asynchronous.  resume=False: a fresh job (first_frame must be 1): every rank zeroes its SUM buffer.
+        resume=True: rank 0's buffer holds the running average after first_frame - 1 render calls (any caller state
+        for first_frame = 1); it is turned back into a sum, A * first_frame (the reference's blend factor is
+        1/(iFrame + 1)), the other ranks start from zero, and the result is the reference's average
+        after first_frame - 1 + total_frames calls."""
+        if first_frame < 1 or (first_frame != 1 and not resume):
+            raise ValueError("a fresh job starts at frame 1; pass resume=True to continue from rank 0's buffer")
         sh = shard_frames(total_frames, self.world, self.rank, first_frame)
         with self.torch.cuda.stream(self.stream):
-            self.buf.zero_()
+            if resume and self.rank == 0:
+                if first_frame > 1:
+                    self.r.scale_target(float(first_frame))
+            else:
+                self.buf.zero_()
             self.r.frame_counter = sh.first_frame - 1
             self.r.render_frames(sh.nframes, sync=False)
             reduce_sum_(self.buf)
-            self.r.finalize_sum(total_frames)
+            self.r.finalize_sum(first_frame - 1 + total_frames)
+            self.r.frame_counter = first_frame - 1 + total_frames
         return self.buf
 
     def close(self):

@@ -13,6 +13,7 @@ namespace {
 
 B200RenderOptions g_options;
 b200pt_context* g_ctx[4] = {nullptr, nullptr, nullptr, nullptr};  // one per reference translation unit
+b200pt_group* g_group[4] = {nullptr, nullptr, nullptr, nullptr};  // num_gpus > 1: the same, sharded over GPUs
 bool g_tile_data_changed = true;                         // tileDataChanged, v4.cpp:1348
 
 [[noreturn]] void die(const char* what, b200pt_context* ctx, int rc)
@@ -22,9 +23,8 @@ bool g_tile_data_changed = true;                         // tileDataChanged, v4.
     std::abort();  // the reference __debugbreak()s on invalid settings (Application.cpp:50-91)
 }
 
-b200pt_context* context_for(int profile)
+b200pt_params params_for(int profile)
 {
-    if (g_ctx[profile]) return g_ctx[profile];
     b200pt_params p;
     int rc = b200pt_default_params(profile, &p);
     if (rc != B200PT_OK) die("b200pt_default_params", nullptr, rc);
@@ -36,22 +36,51 @@ b200pt_context* context_for(int profile)
         p.env_sampler = g_options.use_random_jitter_texture_sampling ? B200PT_SAMPLER_RANDOM : B200PT_SAMPLER_BILINEAR;
         p.output_to_screen = g_options.output_to_screen;
     }
-    rc = b200pt_create(&p, &g_ctx[profile]);
+    return p;
+}
+
+b200pt_context* context_for(int profile)
+{
+    if (g_ctx[profile]) return g_ctx[profile];
+    const b200pt_params p = params_for(profile);
+    const int rc = b200pt_create(&p, &g_ctx[profile]);
     if (rc != B200PT_OK) die("b200pt_create (a B200 is required; there is no CPU fallback)", nullptr, rc);
     return g_ctx[profile];
+}
+
+b200pt_group* group_for(int profile)
+{
+    if (g_group[profile]) return g_group[profile];
+    const b200pt_params p = params_for(profile);
+    int32_t devices[16];
+    const int n = g_options.num_gpus > 16 ? 16 : g_options.num_gpus;
+    for (int i = 0; i < n; i++) devices[i] = g_options.device + i;
+    const int rc = b200pt_group_create(&p, devices, n, g_options.sharding ? B200PT_SHARD_TILES : B200PT_SHARD_SPP,
+                                       g_options.combine ? B200PT_COMBINE_PEER : B200PT_COMBINE_NCCL, &g_group[profile]);
+    if (rc != B200PT_OK) die("b200pt_group_create (num_gpus B200s are required; there is no CPU fallback)", nullptr, rc);
+    return g_group[profile];
 }
 
 void render(int profile, f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture,
             void* ScreenBufferData, i32 NumFrames)
 {
-    b200pt_context* ctx = context_for(profile);
     b200pt_texture t;
     t.Data = Texture.Data;
     t.Width = Texture.Width;
     t.Height = Texture.Height;
     t.Components = Texture.Components;
-    const int rc = b200pt_render_host(ctx, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, t, ScreenBufferData, NumFrames);
-    if (rc != B200PT_OK) die("b200pt_render_host", ctx, rc);
+    if (g_options.num_gpus > 1) {
+        b200pt_group* grp = group_for(profile);
+        const int rc = b200pt_group_render_host(grp, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, t, ScreenBufferData, NumFrames);
+        if (rc != B200PT_OK) {
+            std::fprintf(stderr, "b200pt: b200pt_group_render_host failed: %s: %s\n", b200pt_error_string(rc), b200pt_group_last_error(grp));
+            std::abort();
+        }
+    } else {
+        b200pt_context* ctx = context_for(profile);
+        const int rc = b200pt_render_host(ctx, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, t, ScreenBufferData, NumFrames);
+        if (rc != B200PT_OK) die("b200pt_render_host", ctx, rc);
+    }
     g_tile_data_changed = false;
 }
 
@@ -170,9 +199,10 @@ void WriteImage(char* filename, i32 width, i32 height, i32 components, void* dat
 B200RenderStats B200GetRenderStats(int variant)
 {
     B200RenderStats s{};
-    if (variant < 0 || variant > 3 || !g_ctx[variant]) return s;
+    if (variant < 0 || variant > 3 || (!g_ctx[variant] && !g_group[variant])) return s;
     b200pt_counters c;
-    if (b200pt_get_counters(g_ctx[variant], &c) == B200PT_OK) {
+    if (g_group[variant] ? b200pt_group_get_counters(g_group[variant], &c, &s.combine_ms) == B200PT_OK
+                         : b200pt_get_counters(g_ctx[variant], &c) == B200PT_OK) {
         s.last_render_ms = c.last_render_ms;
         s.paths = c.paths;
         s.segments = c.segments;

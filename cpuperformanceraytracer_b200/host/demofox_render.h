@@ -46,6 +46,12 @@ struct B200RenderOptions {
     int use_env_cubemap = USE_ENV_CUBEMAP;
     int use_random_jitter_texture_sampling = USE_RANDOM_JITTER_TEXTURE_SAMPLING;
     int output_to_screen = OUTPUT_TO_SCREEN;
+    // Several GPUs behind the same entry points: the reference fans a render call out to its worker threads below
+    // DemofoxRenderOptV4 (..._optimization_v4.cpp:1696-1721); with num_gpus > 1 the call is sharded over devices
+    // device .. device + num_gpus - 1 of this process (b200pt_group_*, include/b200pt.h).
+    int num_gpus = 1;
+    int sharding = 0;             // 0 = frames of a ...Frames call (spp), 1 = tiles of every frame (bit-identical to 1 GPU)
+    int combine = 0;              // spp: 0 = NCCL reduce, 1 = the library's own kernel over NVLink peer memory
 };
 // must be called before the first render call of a variant (the contexts are created lazily)
 void B200SetRenderOptions(const B200RenderOptions& options);
@@ -86,5 +92,6 @@ void WriteImage(char* filename, i32 width, i32 height, i32 components, void* dat
 struct B200RenderStats {
     double last_render_ms;
     u64 paths, segments, escapes, launches;
+    double combine_ms;  // num_gpus > 1: device time of the last cross-GPU combine step
 };
 B200RenderStats B200GetRenderStats(int variant /*0 = v2, 1 = simt_textured, 2 = opt_v4, 3 = v3_redo*/);

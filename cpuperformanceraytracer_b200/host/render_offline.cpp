@@ -7,6 +7,7 @@
 //   render_offline [--variant v4|v2|simt|v3redo] [--width W --height H --tiles-x X --tiles-y Y]
 //                  [--frames N] [--bounces B] [--env file.hdr | --cubemap px nx py ny pz nz]
 //                  [--bilinear] [--fast] [--per-frame-calls] [--out out.bmp] [--dump-f32 file]
+//                  [--gpus N [--shard spp|tiles] [--combine nccl|peer]] [--device D]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -39,6 +40,10 @@ int main(int argc, char** argv)
         else if (a == "--bilinear") opt.use_random_jitter_texture_sampling = 0;
         else if (a == "--fast") opt.math_mode = 1;
         else if (a == "--per-frame-calls") per_frame_calls = true;
+        else if (a == "--gpus") opt.num_gpus = atoi(next());
+        else if (a == "--device") opt.device = atoi(next());
+        else if (a == "--shard") opt.sharding = std::string(next()) == "tiles" ? 1 : 0;
+        else if (a == "--combine") opt.combine = std::string(next()) == "peer" ? 1 : 0;
         else if (a == "--out") out = next();
         else if (a == "--dump-f32") dump = next();
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }
@@ -86,8 +91,9 @@ int main(int argc, char** argv)
     const double ms = std::chrono::duration<double, std::milli>(t1 - t0).count();
     const B200RenderStats st = B200GetRenderStats(variant == "v2" ? 0 : variant == "simt" ? 1 : variant == "v3redo" ? 3 : 2);
     std::printf("Total render time: %.3f ms, average frame time: %.5f ms (%d frames, %dx%d, %.1f Mpaths/s wall; "
-                "last kernel %.3f ms on device)\n", ms, ms / frames, frames, W, H, (double)W * H * frames / ms * 1e-3,
-                st.last_render_ms);
+                "last kernel %.3f ms on device, %d GPU%s)\n", ms, ms / frames, frames, W, H, (double)W * H * frames / ms * 1e-3,
+                st.last_render_ms, opt.num_gpus, opt.num_gpus > 1 ? "s" : "");
+    if (opt.num_gpus > 1) std::printf("Cross-GPU combine step: %.3f ms on device\n", st.combine_ms);
     if (!dump.empty()) {
         FILE* f = std::fopen(dump.c_str(), "wb");
         if (f) { std::fwrite(RenderTarget.data(), sizeof(f32), RenderTarget.size(), f); std::fclose(f); }

@@ -21,7 +21,7 @@
 extern "C" {
 #endif
 
-#define B200PT_API_VERSION 1
+#define B200PT_API_VERSION 2
 
 typedef struct b200pt_context b200pt_context;
 
@@ -104,7 +104,9 @@ typedef struct b200pt_counters {
     uint64_t segments;  /* scene traces executed by live paths */
     uint64_t escapes;   /* paths that ended on a miss (one env lookup each) */
     uint64_t launches;  /* CUDA kernels launched by this library on this context */
-    double last_render_ms; /* device time of the last b200pt_render_frames, CUDA events */
+    double last_render_ms; /* device time of the most recent finished b200pt_render_frames launch, CUDA events */
+    uint64_t culled_segments; /* part of `segments`: one per path of a pixel whose camera ray provably misses the
+                                 scene (camera culling) -- the kernel ran no scene trace for them */
 } b200pt_counters;
 
 /* Fills *p with the reference's checked-in defaults for `profile`
@@ -184,8 +186,10 @@ int b200pt_resolve_ldr(b200pt_context* ctx, uint32_t* host_dst, int32_t mode, in
 /* Progressive present path -- the windowed loop of ApplicationState::RunApp (Application.cpp:306-375):
  * render nframes (NUM_SAMPLES_PER_FRAME), tone-map (OutputToScreen packing, fused into the render
  * kernel) and copy the u32 frame to pinned host memory asynchronously.  Two frames can be in flight:
- * submit k+1 overlaps the copy of k.  acquire blocks until the oldest submitted frame is in host
- * memory; the returned pointer stays valid until two more submits. */
+ * submit k+1 overlaps the copy of k (a third submit without an acquire fails with B200PT_ERR_NOT_READY).
+ * acquire blocks until the oldest submitted frame is in host memory.  The ring has three slots, so the
+ * returned pointer stays valid -- whatever is submitted meanwhile -- until the NEXT b200pt_present_acquire
+ * (or resize / destroy). */
 int b200pt_present_submit(b200pt_context* ctx, int32_t nframes);
 int b200pt_present_acquire(b200pt_context* ctx, const uint32_t** frame, int32_t* iframe);
 
@@ -205,8 +209,63 @@ int b200pt_set_tile_row_range(b200pt_context* ctx, int32_t first_tile_row, int32
  * TileY.  Consecutive flat indices are contiguous in the buffer.  (0, 0) = all tiles. */
 int b200pt_set_tile_range(b200pt_context* ctx, int32_t first_flat_tile, int32_t num_tiles);
 /* ACCUM_SUM epilogue: target *= 1/(total_frames + 1), the value the reference's running average
- * converges to after total_frames render calls on a zeroed buffer */
+ * reaches after render calls 1..total_frames on a zeroed buffer.  total_frames is
+ * the LAST frame index of the job, not the number of frames of one shard. */
 int b200pt_finalize_sum(b200pt_context* ctx, int32_t total_frames);
+/* target *= factor on the context's stream (ACCUM_SUM prologue of a continued job: a buffer holding the
+ * running average after F frames, times (F + 1), is the sum of those F samples) */
+int b200pt_scale_target(b200pt_context* ctx, float factor);
+
+/* ---- several GPUs of one box behind the same entry points ------------------------------------------
+ * The reference fans one render call out to its worker threads below the entry point
+ * (DemofoxRenderOptV4 -> AddWorkQueueEntry_Custom per tile -> CompleteAllWork_Custom,
+ * ..._optimization_v4.cpp:1696-1721; MakeWorkQueue, work_queue.cpp:81-108).  A group does the same with
+ * GPUs: ONE host process, one context per device, the frames (or tile rows) of a render call sharded
+ * over them, the f32 accumulation buffers combined on device 0 of the group.
+ *   B200PT_SHARD_SPP    every (pixel, iFrame) sample re-seeds its RNG (..._optimization_v4.cpp:1096-1101), so
+ *                       rank r renders a contiguous block of the call's frame range into a SUM buffer; the N
+ *                       buffers are summed into rank 0's and scaled by 1/(iFrame + 1).  Same samples as the
+ *                       sequential render, different summation order (~1e-6 relative, not bit-identical).
+ *                       A continued job (iFrame = F > 0) first turns rank 0's average back into a sum
+ *                       (x (F + 1)), so N more frames give exactly the reference's average after F + N calls.
+ *   B200PT_SHARD_TILES  rank r renders tile rows [a_r, b_r) of every frame with the reference's running
+ *                       average and the contiguous spans are copied into rank 0's buffer: bit-identical to
+ *                       the single-GPU render.
+ * How the SUM buffers meet (B200PT_SHARD_SPP):
+ *   B200PT_COMBINE_NCCL ncclReduce(sum, root 0) over NVLink + one scale kernel on rank 0
+ *   B200PT_COMBINE_PEER one kernel per GPU over NVLink peer memory: rank r sums slice r of all N buffers in
+ *                       rank order (deterministic), scales, and stores the slice straight into rank 0's buffer
+ * libnccl.so.2 is loaded on first use (dlopen); without it B200PT_COMBINE_NCCL fails with B200PT_ERR_NOT_READY. */
+typedef struct b200pt_group b200pt_group;
+enum { B200PT_SHARD_SPP = 0, B200PT_SHARD_TILES = 1 };
+enum { B200PT_COMBINE_NCCL = 0, B200PT_COMBINE_PEER = 1 };
+/* params->device is ignored (devices[] rules); params->accum_mode is chosen by the sharding */
+int b200pt_group_create(const b200pt_params* params, const int32_t* devices, int32_t num_devices, int32_t sharding,
+                        int32_t combine, b200pt_group** out_group);
+int b200pt_group_destroy(b200pt_group* group);
+int b200pt_group_size(b200pt_group* group);
+/* the per-device context (rank 0 holds the image): for set_scene_v4 on every rank, counters, streams */
+b200pt_context* b200pt_group_context(b200pt_group* group, int32_t rank);
+int b200pt_group_set_env(b200pt_group* group, b200pt_texture tex);
+int b200pt_group_resize(b200pt_group* group, int32_t width, int32_t height, int32_t num_tiles_x, int32_t num_tiles_y);
+int b200pt_group_reset(b200pt_group* group);
+int b200pt_group_set_frame_counter(b200pt_group* group, int32_t iframe);
+int b200pt_group_get_frame_counter(b200pt_group* group, int32_t* iframe);
+/* == nframes consecutive render calls of the reference, sharded; asynchronous; the image lives on rank 0 */
+int b200pt_group_render_frames(b200pt_group* group, int32_t nframes);
+int b200pt_group_synchronize(b200pt_group* group);
+int b200pt_group_upload_target(b200pt_group* group, const float* host_src);
+int b200pt_group_download_target(b200pt_group* group, float* host_dst);
+/* b200pt_render_host on a group: host accumulation buffer in, nframes sharded render calls, buffer out */
+int b200pt_group_render_host(b200pt_group* group, float* BufferOut, int32_t BufferWidth, int32_t BufferHeight,
+                             int32_t NumTilesX, int32_t NumTilesY, int32_t TileWidth, int32_t TileHeight,
+                             int32_t NumChannels, b200pt_texture Texture, void* ScreenBufferData, int32_t nframes);
+/* CopyOutputToFile on rank 0's image */
+int b200pt_group_resolve_ldr(b200pt_group* group, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter);
+/* counters summed over the ranks; last_render_ms = the longest rank's last launch; *combine_ms (may be NULL) =
+ * device time of the last combine step (reduce + scale, or span copies) on rank 0's stream */
+int b200pt_group_get_counters(b200pt_group* group, b200pt_counters* out, double* combine_ms);
+const char* b200pt_group_last_error(b200pt_group* group);
 
 /* debug/parity hook: u32 RNG state of every pixel after the last rendered frame's path ended
  * (row-major W*H, row 0 = top); checks wang_hash stream parity bit for bit */

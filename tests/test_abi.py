@@ -27,7 +27,7 @@ def test_header_symbols_exported():
     for name in declared:
         assert hasattr(lib, name), f"{name} declared in b200pt.h but not exported"
     assert sorted(api.ABI_SYMBOLS) == declared
-    assert lib.b200pt_api_version() == 1
+    assert lib.b200pt_api_version() == 2
 
 
 def test_built_in_scenes_match_the_specialised_kernels_tables():

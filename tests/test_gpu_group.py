@@ -1,0 +1,152 @@
+"""b200pt_group_*: several ranks behind one set of render entry points, in one process, without torch.
+
+The sharding and combine logic is exercised on ONE GPU too: a group may place several ranks (contexts with their own
+streams and SUM buffers) on the same device -- legal for tile sharding and for the library's own peer-memory combine
+kernel.  With >= 2 GPUs the same tests run across devices, NCCL included.
+
+Bars: tile sharding is BIT-IDENTICAL to the single-context render (hence to the oracle); spp sharding renders the same
+samples in another summation order: <= 3e-6 relative (stated in include/b200pt.h)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from cpuperformanceraytracer_b200 import api  # noqa: E402
+
+
+def _ngpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _device_sets():
+    sets = [("3 ranks on gpu 0", [0, 0, 0])]
+    n = _ngpus()
+    if n >= 2:
+        sets.append((f"{min(n, 4)} gpus", list(range(min(n, 4)))))
+    return sets
+
+
+W, H, NTX, NTY, BOUNCES = 192, 96, 2, 4, 8
+
+
+def _sequential(frames, profile=api.PROFILE_V2, env=None, **kw):
+    with api.Renderer(profile=profile, num_bounces=BOUNCES, **kw) as r:
+        if env is not None:
+            r.set_env(env)
+        r.resize(W, H, NTX, NTY)
+        out = []
+        for f in frames:
+            r.render_frames(f)
+            out.append(r.download_target())
+        return out
+
+
+@pytest.mark.parametrize("label,devices", _device_sets(), ids=[s[0] for s in _device_sets()])
+def test_tile_shard_group_is_bit_identical(oracle, label, devices):
+    seq = _sequential([7, 5])
+    o, _ = oracle.render(0, W, H, NTX, NTY, BOUNCES, 12)
+    assert np.array_equal(seq[1], o)
+    with api.Group(devices, sharding=api.SHARD_TILES, profile=api.PROFILE_V2, num_bounces=BOUNCES) as g:
+        g.resize(W, H, NTX, NTY)
+        g.render_frames(7)
+        assert np.array_equal(g.download_target(), seq[0])
+        g.render_frames(5)  # continued: every rank keeps the running average of its own tiles
+        assert np.array_equal(g.download_target(), seq[1])
+        assert g.frame_counter == 12
+        c = g.counters()
+        assert c["paths"] == W * H * 12
+        # the reference-facing call on a host buffer: spans travel over each rank's own link
+        buf = np.zeros(W * H * 3, dtype=np.float32)
+        g.frame_counter = 0
+        g.render_host(buf, W, H, NTX, NTY, 7)
+        assert np.array_equal(buf, seq[0])
+        g.render_host(buf, W, H, NTX, NTY, 5)
+        assert np.array_equal(buf, seq[1])
+        # tone-mapped output of the gathered image == single context
+        g.reset()
+        g.render_frames(12)
+        ldr = g.resolve_ldr()
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES) as r:
+        r.resize(W, H, NTX, NTY)
+        r.render_frames(12)
+        assert np.array_equal(ldr, r.resolve_ldr())
+
+
+@pytest.mark.parametrize("label,devices", _device_sets(), ids=[s[0] for s in _device_sets()])
+def test_spp_shard_group_peer_combine(label, devices):
+    seq = _sequential([24, 9])
+    with api.Group(devices, sharding=api.SHARD_SPP, combine=api.COMBINE_PEER, profile=api.PROFILE_V2, num_bounces=BOUNCES) as g:
+        g.resize(W, H, NTX, NTY)
+        g.render_frames(24)
+        a = g.download_target()
+        assert np.allclose(a, seq[0], rtol=3e-6, atol=3e-6)
+        g.render_frames(9)  # continued job: the average is turned back into a sum first
+        b = g.download_target()
+        assert np.allclose(b, seq[1], rtol=3e-6, atol=3e-6)
+        # deterministic: the combine adds the partial sums in rank order
+        g.reset()
+        g.render_frames(24)
+        assert np.array_equal(g.download_target(), a)
+        c = g.counters()
+        assert c["paths"] == W * H * (24 + 9 + 24) and c["combine_ms"] > 0.0
+        # fewer frames than ranks: some ranks render nothing
+        g.reset()
+        g.render_frames(2)
+        with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES) as r:
+            r.resize(W, H, NTX, NTY)
+            r.render_frames(2)
+            assert np.allclose(g.download_target(), r.download_target(), rtol=3e-6, atol=3e-6)
+        # host-buffer call, continued from a non-empty accumulation state
+        buf = seq[0].copy()
+        g.frame_counter = 24
+        g.render_host(buf, W, H, NTX, NTY, 9)
+        assert np.allclose(buf, seq[1], rtol=3e-6, atol=3e-6)
+
+
+def test_group_with_env_profile(oracle):
+    env = oracle.synthetic_env(64, 384)
+    seq = _sequential([10], profile=api.PROFILE_OPT_V4, env=env, env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM)[0]
+    o, _ = oracle.render(2, W, H, NTX, NTY, BOUNCES, 10, env=env, env_kind=2, env_sampler=2)
+    assert np.array_equal(seq, o)
+    for sharding in (api.SHARD_TILES, api.SHARD_SPP):
+        with api.Group([0, 0], sharding=sharding, combine=api.COMBINE_PEER, profile=api.PROFILE_OPT_V4, num_bounces=BOUNCES,
+                       env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM) as g:
+            g.set_env(env)
+            g.resize(W, H, NTX, NTY)
+            g.render_frames(10)
+            out = g.download_target()
+        if sharding == api.SHARD_TILES:
+            assert np.array_equal(out, o)
+        else:
+            assert np.allclose(out, o, rtol=3e-6, atol=3e-6)
+
+
+@pytest.mark.skipif(_ngpus() < 2, reason="NCCL wants one device per rank: needs at least 2 GPUs")
+def test_spp_shard_group_nccl():
+    seq = _sequential([24, 9])
+    n = min(_ngpus(), 4)
+    with api.Group(list(range(n)), sharding=api.SHARD_SPP, combine=api.COMBINE_NCCL, profile=api.PROFILE_V2, num_bounces=BOUNCES) as g:
+        g.resize(W, H, NTX, NTY)
+        g.render_frames(24)
+        assert np.allclose(g.download_target(), seq[0], rtol=3e-6, atol=3e-6)
+        g.render_frames(9)
+        assert np.allclose(g.download_target(), seq[1], rtol=3e-6, atol=3e-6)
+
+
+def test_group_argument_checking():
+    import ctypes
+    lib = api.load_library()
+    p = api.default_params(api.PROFILE_V2)
+    g = ctypes.c_void_p()
+    devs = (ctypes.c_int32 * 2)(0, 0)
+    assert lib.b200pt_group_create(ctypes.byref(p), devs, 0, 0, 0, ctypes.byref(g)) == 1
+    assert lib.b200pt_group_create(ctypes.byref(p), devs, 2, 7, 0, ctypes.byref(g)) == 1
+    # NCCL cannot place two ranks on one device
+    assert lib.b200pt_group_create(ctypes.byref(p), devs, 2, api.SHARD_SPP, api.COMBINE_NCCL, ctypes.byref(g)) == 1
+    with api.Group([0], profile=api.PROFILE_V2) as one:
+        with pytest.raises(api.B200PTError):
+            one.render_frames(1)  # resize first

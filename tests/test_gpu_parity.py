@@ -293,6 +293,32 @@ def test_present_ring_frames_are_the_reference_screen_frames(oracle):
         assert np.array_equal(img, oracle.resolve_ldr(buf, W, H, ntx, nty, mode=1)), k
 
 
+def test_present_ring_zero_copy_view_survives_the_next_submits():
+    """The pointer b200pt_present_acquire hands out stays valid until the NEXT acquire, whatever is submitted
+    meanwhile (three host slots): a zero-copy consumer holds frame k while frames k+1 and k+2 render and copy."""
+    import time
+    W, H, ntx, nty = 256, 128, 4, 4
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=8, output_to_screen=True) as r:
+        r.resize(W, H, ntx, nty)
+        r.present_submit(1)
+        for k in range(1, 8):                                  # every phase of the 3-slot rotation
+            view, iframe = r.present_acquire(copy=False)       # frame k, a view of pinned memory
+            assert iframe == k
+            snapshot = view.copy()
+            r.present_submit(1)                                # frames k+1 and k+2 go through the ring
+            r.present_submit(1)
+            r.synchronize()
+            time.sleep(0.02)                                   # let both asynchronous copies land
+            assert np.array_equal(view, snapshot), k           # ... and frame k is still frame k
+            nxt, fnext = r.present_acquire()                   # k+1 (the view of k is dead from here on)
+            assert fnext == k + 1 and not np.array_equal(nxt, snapshot)
+            # leave exactly one frame (k+2) in flight for the next round: skip it and submit the following one
+            skipped, fs = r.present_acquire()
+            assert fs == k + 2
+            r.frame_counter = k
+            r.present_submit(1)
+
+
 def test_full_size_bit_exact_vs_oracle(oracle):
     """BASELINE config 2 geometry (1920x1080, tiles 10x15, 8 bounces) at a bounded spp: the whole f32
     buffer, the RNG states and the counters equal the oracle's, bit for bit (the oracle takes ~10 s)."""

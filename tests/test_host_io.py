@@ -40,6 +40,17 @@ def load_hdr(io, path):
     return a
 
 
+def load_cubemap(io, paths):
+    """six face files (px nx py ny pz nz) -> the (6*face, face, 3) atlas LoadCubemapTexture builds, or None"""
+    arr = (ctypes.c_char_p * 6)(*[str(f).encode() for f in paths])
+    data, cw, ch = ctypes.POINTER(ctypes.c_float)(), ctypes.c_int(), ctypes.c_int()
+    if io.b200pt_io_load_cubemap(arr, ctypes.byref(data), ctypes.byref(cw), ctypes.byref(ch)) != 0:
+        return None
+    a = np.ctypeslib.as_array(data, shape=(ch.value, cw.value, 3)).copy()
+    io.b200pt_io_free(data)
+    return a
+
+
 def rgbe_encode(img):
     """float (H, W, 3) top-down -> RGBE bytes (H, W, 4), standard Radiance encoding."""
     m = img.max(axis=2)
