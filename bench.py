@@ -96,12 +96,12 @@ def measured_ncu_utilisation():
     out["alu_pipe_pct"] = m.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active")
     out["xu_pipe_pct"] = m.get("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active")
     out["active_lanes"] = m.get("smsp__thread_inst_executed_per_inst_executed.ratio")
-    fadd = m.get("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum")
-    fmul = m.get("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum")
-    ffma = m.get("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum")
-    cyc = m.get("sm__cycles_elapsed.avg")
-    if None not in (fadd, fmul, ffma, cyc) and cyc > 0:
-        out["executed_fp32_frac"] = (fadd + fmul + 2.0 * ffma) / (cyc * 148 * 128 * 2)
+    # thread-level FP32 instructions per elapsed cycle, summed over the chip
+    fadd = m.get("smsp__sass_thread_inst_executed_op_fadd_pred_on.sum.per_cycle_elapsed")
+    fmul = m.get("smsp__sass_thread_inst_executed_op_fmul_pred_on.sum.per_cycle_elapsed")
+    ffma = m.get("smsp__sass_thread_inst_executed_op_ffma_pred_on.sum.per_cycle_elapsed")
+    if None not in (fadd, fmul, ffma):
+        out["executed_fp32_frac"] = (fadd + fmul + 2.0 * ffma) / (148 * 128 * 2)
     else:
         out["executed_fp32_frac"] = None
     return out

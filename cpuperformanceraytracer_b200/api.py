@@ -19,6 +19,7 @@ ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
 SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
 ACCUM_RUNNING_AVERAGE, ACCUM_SUM = 0, 1
 LDR_FILE_RGBA, LDR_SCREEN_BGRA = 0, 1
+SCHED_DEFAULT, SCHED_LANE, SCHED_SORTED = 0, 1, 2
 
 # every symbol include/b200pt.h declares (tests/test_abi.py checks the library exports them all)
 ABI_SYMBOLS = [
@@ -27,7 +28,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
+    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_present_blocking", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
     "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_scale_target",
     "b200pt_group_create", "b200pt_group_destroy", "b200pt_group_size", "b200pt_group_context", "b200pt_group_set_env",
     "b200pt_group_resize", "b200pt_group_reset", "b200pt_group_set_frame_counter", "b200pt_group_get_frame_counter",
@@ -50,7 +51,7 @@ class Params(ctypes.Structure):
                 ("math_mode", ctypes.c_int32), ("num_bounces", ctypes.c_int32), ("env_kind", ctypes.c_int32),
                 ("env_sampler", ctypes.c_int32), ("accum_mode", ctypes.c_int32), ("output_to_screen", ctypes.c_int32),
                 ("disable_camera_culling", ctypes.c_int32), ("generic_scene_tables", ctypes.c_int32),
-                ("reserved", ctypes.c_int32 * 5)]
+                ("scheduler", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
 
 
 class Counters(ctypes.Structure):
@@ -103,6 +104,7 @@ def load_library():
     L.b200pt_set_scene_v4.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.b200pt_present_submit.argtypes = [vp, i32]
     L.b200pt_present_acquire.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(i32)]
+    L.b200pt_present_blocking.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_uint32), i32]
     L.b200pt_download_rng_state.argtypes = [vp, ctypes.POINTER(ctypes.c_uint32)]
     L.b200pt_get_counters.argtypes = [vp, ctypes.POINTER(Counters)]
     fpp = ctypes.POINTER(ctypes.c_float)
@@ -153,7 +155,7 @@ class Renderer:
 
     def __init__(self, profile=PROFILE_V2, math_mode=MATH_PARITY, num_bounces=-1, device=0, env_kind=None,
                  env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False,
-                 disable_camera_culling=False, generic_scene_tables=False):
+                 disable_camera_culling=False, generic_scene_tables=False, scheduler=SCHED_DEFAULT):
         self._lib = load_library()
         self._ctx = ctypes.c_void_p()
         p = default_params(profile)
@@ -161,6 +163,7 @@ class Renderer:
         p.accum_mode, p.output_to_screen = accum_mode, int(bool(output_to_screen))
         p.disable_camera_culling = int(bool(disable_camera_culling))
         p.generic_scene_tables = int(bool(generic_scene_tables))
+        p.scheduler = int(scheduler)
         if env_kind is not None:
             p.env_kind = env_kind
         if env_sampler is not None:
@@ -292,6 +295,14 @@ class Renderer:
         a = np.ctypeslib.as_array(ptr, shape=(self.height, self.width))
         return (a.copy() if copy else a), fr.value
 
+    def present_blocking(self, out, nframes=1, bands=0):
+        """nframes render calls + fused tone map + band-pipelined copy: `out` ((H, W) uint32, ideally page-locked)
+        holds the screen frame when the call returns"""
+        assert out.dtype == np.uint32 and out.flags["C_CONTIGUOUS"] and out.size == self.height * self.width
+        rc = self._lib.b200pt_present_blocking(self._ctx, int(nframes), out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)), int(bands))
+        self._check(rc, "b200pt_present_blocking")
+        return out
+
     def rng_state(self):
         out = np.empty((self.height, self.width), dtype=np.uint32)
         rc = self._lib.b200pt_download_rng_state(self._ctx, out.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
@@ -354,11 +365,12 @@ class Group:
     tiles (SHARD_TILES) of every render call are sharded over `devices`; the image lives on devices[0]."""
 
     def __init__(self, devices, sharding=SHARD_SPP, combine=COMBINE_NCCL, profile=PROFILE_V2, math_mode=MATH_PARITY,
-                 num_bounces=-1, env_kind=None, env_sampler=None, output_to_screen=False):
+                 num_bounces=-1, env_kind=None, env_sampler=None, output_to_screen=False, scheduler=SCHED_DEFAULT):
         self._lib = load_library()
         self._g = ctypes.c_void_p()
         p = default_params(profile)
         p.math_mode, p.num_bounces = math_mode, num_bounces
+        p.scheduler = int(scheduler)
         p.output_to_screen = int(bool(output_to_screen))
         if env_kind is not None:
             p.env_kind = env_kind

@@ -37,12 +37,14 @@ UNITS = [
     # (source, object, extra flags)
     (os.path.join(CSRC, "pt_kernels_parity.cu"), "pt_kernels_parity.o", IEEE),
     (os.path.join(CSRC, "pt_kernels_fast.cu"), "pt_kernels_fast.o", ["--fmad=true"]),
+    (os.path.join(CSRC, "pt_kernels_parity_sorted.cu"), "pt_kernels_parity_sorted.o", IEEE),
+    (os.path.join(CSRC, "pt_kernels_fast_sorted.cu"), "pt_kernels_fast_sorted.o", ["--fmad=true"]),
     (os.path.join(CSRC, "pt_post.cu"), "pt_post.o", IEEE),
     (os.path.join(CSRC, "b200pt_capi.cu"), "b200pt_capi.o", IEEE),
     (os.path.join(CSRC, "b200pt_group.cu"), "b200pt_group.o", IEEE),
     (os.path.join(HOST, "scene_setup.cpp"), "scene_setup.o", IEEE),
 ]
-HEADERS = [os.path.join(CSRC, f) for f in ("pt_common.cuh", "pt_device.cuh", "pm_math.cuh", "pt_tonemap.cuh", "b200pt_context.h")] + [
+HEADERS = [os.path.join(CSRC, f) for f in ("pt_common.cuh", "pt_device.cuh", "pm_math.cuh", "pt_tonemap.cuh", "b200pt_context.h", "pt_wavefront.cuh")] + [
     os.path.join(HOST, "scene_setup.h"), os.path.join(ROOT, "include", "b200pt.h")]
 
 

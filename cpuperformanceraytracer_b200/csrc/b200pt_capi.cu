@@ -3,6 +3,7 @@
 // table: demofox_path_tracing_optimization_v4.cpp:34,378,386,1343) plus the HBM copies of the
 // caller's buffers.  No CPU rendering path exists here: without a usable GPU every call fails.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -14,6 +15,14 @@ bool uses_env(const b200pt_params& p)
 {
     if (p.profile == B200PT_PROFILE_SIMT_TEXTURED || p.profile == B200PT_PROFILE_V3_REDO) return true;
     return p.profile == B200PT_PROFILE_OPT_V4 && p.env_kind != B200PT_ENV_NONE;
+}
+
+// Which scheduler a profile runs with unless the caller says otherwise: the faster one as measured on B200
+// (DESIGN.md section 5).
+int default_scheduler(int profile)
+{
+    (void)profile;
+    return B200PT_SCHED_LANE;
 }
 
 LaunchConfig launch_config(const b200pt_context* c)
@@ -207,6 +216,27 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
         return B200PT_ERR_CUDA;
     }
     c->blocks_per_sm = bps;
+    // the CTA-sorted scheduler: asked for by the caller, by the environment (A/B measurements), or the profile's default
+    int sched = c->params.scheduler;
+    if (const char* env = std::getenv("B200PT_SCHEDULER")) {
+        if (!std::strcmp(env, "lane")) sched = B200PT_SCHED_LANE;
+        else if (!std::strcmp(env, "sorted")) sched = B200PT_SCHED_SORTED;
+    }
+    if (sched == B200PT_SCHED_DEFAULT) sched = default_scheduler(c->params.profile);
+    if (sched != B200PT_SCHED_LANE && sched != B200PT_SCHED_SORTED) {
+        b200pt_destroy(c);
+        return B200PT_ERR_INVALID_ARGUMENT;
+    }
+    c->sorted = sched == B200PT_SCHED_SORTED;
+    if (c->sorted) {
+        bps = 0;
+        e = (c->params.math_mode == B200PT_MATH_PARITY) ? occupancy_sorted_parity(lc, &bps) : occupancy_sorted_fast(lc, &bps);
+        if (e != cudaSuccess || bps <= 0) {
+            b200pt_destroy(c);
+            return B200PT_ERR_CUDA;
+        }
+        c->blocks_per_sm_sorted = bps;
+    }
     *out_ctx = c;
     return B200PT_OK;
 }
@@ -439,7 +469,9 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     // persistent grid: every SM holds blocks_per_sm resident CTAs; warps pull 32-pixel items
     const int warps_per_block = lc.block / 32;
     const int max_useful_blocks = (rp.num_items + warps_per_block - 1) / warps_per_block;
-    lc.grid = c->sm_count * c->blocks_per_sm;
+    // the sorted kernel packs the bounce count into 8 bits and the pixel coordinates into 16 each
+    const bool sorted = c->sorted && rp.num_bounces <= 250 && rp.width <= 65535 && rp.height <= 65535;
+    lc.grid = c->sm_count * (sorted ? c->blocks_per_sm_sorted : c->blocks_per_sm);
     if (lc.grid > max_useful_blocks) lc.grid = max_useful_blocks;
     if (lc.grid < 1) lc.grid = 1;
 
@@ -447,9 +479,13 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     const unsigned ts = c->timing_slot;
     c->timing_slot ^= 1u;
     CUDA_TRY(c, cudaEventRecord(c->ev0[ts], c->stream));
-    cudaError_t e = (c->params.math_mode == B200PT_MATH_PARITY)
-                        ? launch_render_parity(lc, rp, c->scenes, c->stream)
-                        : launch_render_fast(lc, rp, c->scenes, c->stream);
+    cudaError_t e;
+    if (sorted)
+        e = (c->params.math_mode == B200PT_MATH_PARITY) ? launch_render_sorted_parity(lc, rp, c->scenes, c->stream)
+                                                        : launch_render_sorted_fast(lc, rp, c->scenes, c->stream);
+    else
+        e = (c->params.math_mode == B200PT_MATH_PARITY) ? launch_render_parity(lc, rp, c->scenes, c->stream)
+                                                        : launch_render_fast(lc, rp, c->scenes, c->stream);
     CUDA_TRY(c, e);
     CUDA_TRY(c, cudaEventRecord(c->ev1[ts], c->stream));
     c->timing_pending[ts] = true;
@@ -616,6 +652,59 @@ int b200pt_present_acquire(b200pt_context* c, const uint32_t** frame, int32_t* i
     *frame = c->h_ring[slot];
     if (iframe) *iframe = c->ring_frame[slot];
     c->acquired++;
+    return B200PT_OK;
+}
+
+int b200pt_present_blocking(b200pt_context* c, int32_t nframes, uint32_t* host_frame, int32_t bands)
+{
+    if (!c || nframes <= 0 || !host_frame || bands < -1) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    if (c->num_tiles > 0) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "a tile range is set: the blocking present renders the whole image");
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
+    if (bands == -1) {
+        // zero-copy: the kernel's tone-map epilogue stores every finished pixel straight into the caller's page-locked,
+        // device-mapped frame over PCIe -- no copy operation at all, the transfer overlaps the render
+        void* dptr = nullptr;
+        if (cudaHostGetDevicePointer(&dptr, host_frame, 0) != cudaSuccess) {
+            cudaGetLastError();
+            return fail(c, B200PT_ERR_INVALID_ARGUMENT, "bands = -1 needs a page-locked, device-mapped host frame");
+        }
+        const int rc = render_frames_impl(c, nframes, static_cast<uint32_t*>(dptr));
+        if (rc != B200PT_OK) return rc;
+        CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+        return B200PT_OK;
+    }
+    if (bands == 0) bands = 2;  // measured on B200 (1080p, 1 frame): 0.345 / 0.300 / 0.301 / 0.321 ms for 1 / 2 / 3 / 4 bands
+    if (bands > c->nty) bands = c->nty;
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));  // the present ring may still be reading d_screen (slot 0)
+    const int first_iframe = c->iframe;
+    const size_t row_bytes = (size_t)c->width * sizeof(uint32_t);
+    int rc = B200PT_OK;
+    for (int b = 0; b < bands && rc == B200PT_OK; b++) {
+        const int row0 = (int)((long long)c->nty * b / bands), row1 = (int)((long long)c->nty * (b + 1) / bands);
+        if (row1 == row0) continue;
+        c->first_tile = row0 * c->ntx;
+        c->num_tiles = (row1 - row0) * c->ntx;
+        c->iframe = first_iframe;  // every band renders the same frames
+        rc = render_frames_impl(c, nframes, c->d_screen);
+        if (rc != B200PT_OK) break;
+        const int slot = b % kRingSlots;
+        const size_t off = (size_t)row0 * c->tile_h * c->width;  // first pixel of the band in the row-major frame
+        const size_t bytes = (size_t)(row1 - row0) * c->tile_h * row_bytes;
+        cudaError_t e = cudaEventRecord(c->render_done[slot], c->stream);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(c->copy_stream, c->render_done[slot], 0);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(host_frame + off, c->d_screen + off, bytes, cudaMemcpyDeviceToHost, c->copy_stream);
+        if (e != cudaSuccess) {
+            c->first_tile = c->num_tiles = 0;
+            CUDA_TRY(c, e);
+        }
+    }
+    c->first_tile = c->num_tiles = 0;
+    // the bands' launches counted every path once; the frame counter advances once
+    c->iframe = first_iframe + nframes;
+    if (rc != B200PT_OK) return rc;
+    CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
     return B200PT_OK;
 }
 

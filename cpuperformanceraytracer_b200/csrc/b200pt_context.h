@@ -60,6 +60,8 @@ struct b200pt_context {
     int iframe = 0;
     int first_tile = 0, num_tiles = 0;  // flat tile range rendered by this context (0, 0 = all tiles)
     int blocks_per_sm = 0;
+    bool sorted = false;           // B200PT_SCHED_SORTED: pt_render_sorted_kernel instead of pt_render_kernel
+    int blocks_per_sm_sorted = 0;
     uint64_t paths = 0, launches = 0;
     double last_render_ms = 0.0;
     std::string last_error;

@@ -199,6 +199,11 @@ cudaError_t launch_render_parity(const LaunchConfig& lc, const RenderParams& rp,
 cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
 cudaError_t occupancy_parity(const LaunchConfig& lc, int* blocks_per_sm);
 cudaError_t occupancy_fast(const LaunchConfig& lc, int* blocks_per_sm);
+// the CTA-sorted variant (pt_wavefront.cuh), in pt_kernels_parity_sorted.cu / pt_kernels_fast_sorted.cu
+cudaError_t launch_render_sorted_parity(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
+cudaError_t launch_render_sorted_fast(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
+cudaError_t occupancy_sorted_parity(const LaunchConfig& lc, int* blocks_per_sm);
+cudaError_t occupancy_sorted_fast(const LaunchConfig& lc, int* blocks_per_sm);
 
 // pt_post.cu
 cudaError_t launch_resolve_ldr(const float* target, uint32_t* out, int width, int height, int tile_w, int tile_h,

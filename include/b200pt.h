@@ -70,6 +70,15 @@ enum {
                                          a sum-reduce and b200pt_finalize_sum() */
 };
 
+/* Mapping of paths to GPU threads; the reference's counterpart is its tile queue + 8-wide masked lanes
+ * (work_queue.cpp:7-66, RenderTile ..._optimization_v4.cpp:1189-1252).  Bit-identical results either way. */
+enum {
+    B200PT_SCHED_DEFAULT = 0,  /* the measured-faster one for the profile (environment variable B200PT_SCHEDULER=lane|sorted overrides) */
+    B200PT_SCHED_LANE = 1,     /* one pixel per lane for the whole launch; a finished path restarts in place */
+    B200PT_SCHED_SORTED = 2    /* every loop trip the CTA sorts its 256 paths by what they need next (shade / miss + restart),
+                                  so warps are role-pure; per-pixel state lives in shared memory */
+};
+
 /* ScreenBufferData packing, ..._optimization_v4.cpp:1285-1290 (screen) / :1321-1325 (file) */
 enum { B200PT_LDR_FILE_RGBA = 0, B200PT_LDR_SCREEN_BGRA = 1 };
 
@@ -96,7 +105,8 @@ typedef struct b200pt_params {
                                        misses every primitive (A/B measurements; results are identical) */
     int32_t generic_scene_tables;   /* 1: read the Cornell vertices from the scene table instead of the
                                        compile-time specialisation (A/B measurements; results are identical) */
-    int32_t reserved[5];
+    int32_t scheduler;              /* B200PT_SCHED_*: how paths are mapped to threads (results are identical) */
+    int32_t reserved[4];
 } b200pt_params;
 
 typedef struct b200pt_counters {
@@ -192,6 +202,15 @@ int b200pt_resolve_ldr(b200pt_context* ctx, uint32_t* host_dst, int32_t mode, in
  * (or resize / destroy). */
 int b200pt_present_submit(b200pt_context* ctx, int32_t nframes);
 int b200pt_present_acquire(b200pt_context* ctx, const uint32_t** frame, int32_t* iframe);
+/* The same loop iteration as ONE blocking call (Application.cpp:330-360: Render, then the frame is in BackBuffer.Memory):
+ * nframes render calls with the tone map fused into the kernel, the u32 frame (OutputToScreen packing) in
+ * host_frame when the call returns.  The image is rendered in `bands` groups of tile rows (0 = the library's choice);
+ * the rows of a finished band are contiguous in the row-major frame, so their copy to the host runs on the copy
+ * engine while the next band renders: latency ~ render + one band's copy instead of render + tone map + whole copy.
+ * host_frame should be page-locked (cudaHostAlloc / cudaHostRegister); pageable memory works but is copied
+ * synchronously by the driver.  bands = -1: no copy operation at all -- the kernel stores every finished pixel
+ * straight into the (page-locked, device-mapped) host frame over PCIe. */
+int b200pt_present_blocking(b200pt_context* ctx, int32_t nframes, uint32_t* host_frame, int32_t bands);
 
 /* multi-GPU plumbing: render into / reduce over a caller-owned device buffer (e.g. the storage of
  * a tensor handed to an NCCL all-reduce).  Pass NULL to go back to the internal buffer. */

@@ -100,7 +100,7 @@ def test_render_offline_simt_and_v3redo(oracle, io, tmp_path):
     o, _ = oracle.render(oracle.PROFILE_SIMT_TEXTURED, W, H, NTX, NTY, 4, FRAMES + 2, env=tex, env_kind=oracle.ENV_EQUIRECT)
     assert np.array_equal(g, o)
     g, _ = run_cli(tmp_path, "--variant", "v3redo", "--env", path)
-    o, _ = oracle.render(oracle.PROFILE_V3_REDO, W, H, NTX, NTY, 8, FRAMES + 2, env=tex, env_kind=oracle.ENV_EQUIRECT,
+    o, _ = oracle.render(oracle.PROFILE_V3REDO, W, H, NTX, NTY, 8, FRAMES + 2, env=tex, env_kind=oracle.ENV_EQUIRECT,
                          env_sampler=oracle.SAMPLER_BILINEAR)
     assert np.array_equal(g, o)
 

@@ -293,6 +293,29 @@ def test_present_ring_frames_are_the_reference_screen_frames(oracle):
         assert np.array_equal(img, oracle.resolve_ldr(buf, W, H, ntx, nty, mode=1)), k
 
 
+def test_present_blocking_is_the_reference_screen_frame(oracle):
+    """b200pt_present_blocking: render + fused tone map + band-pipelined copy == OutputToScreen of the oracle's buffer,
+    for any band count, and the accumulation buffer / frame counter advance exactly once"""
+    W, H, ntx, nty = 192, 120, 3, 5
+    cube = oracle.synthetic_env(32, 192)
+    buf = np.zeros(W * H * 3, dtype=np.float32)
+    with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=8, env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM) as r:
+        r.set_env(cube)
+        r.resize(W, H, ntx, nty)
+        import torch
+        frame = torch.zeros((H, W), dtype=torch.int32).pin_memory().numpy().view(np.uint32)  # page-locked + device-mapped
+        k = 0
+        for bands, n in ((0, 1), (1, 2), (3, 1), (5, 3), (64, 1), (-1, 1), (-1, 2)):
+            r.present_blocking(frame, nframes=n, bands=bands)
+            buf, _ = oracle.render(oracle.PROFILE_V4, W, H, ntx, nty, 8, n, first_frame=k + 1, env=cube, env_kind=2, env_sampler=2,
+                                   target=buf)
+            k += n
+            assert r.frame_counter == k
+            assert np.array_equal(frame, oracle.resolve_ldr(buf, W, H, ntx, nty, mode=1)), (bands, n)
+            assert np.array_equal(r.download_target(), buf)
+        assert r.counters()["paths"] == W * H * k
+
+
 def test_present_ring_zero_copy_view_survives_the_next_submits():
     """The pointer b200pt_present_acquire hands out stays valid until the NEXT acquire, whatever is submitted
     meanwhile (three host slots): a zero-copy consumer holds frame k while frames k+1 and k+2 render and copy."""
