@@ -29,9 +29,9 @@ ABI_SYMBOLS = [
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
     "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_present_blocking", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
-    "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_scale_target",
+    "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_scale_target", "b200pt_scale_target_span",
     "b200pt_group_create", "b200pt_group_destroy", "b200pt_group_size", "b200pt_group_context", "b200pt_group_set_env",
-    "b200pt_group_resize", "b200pt_group_reset", "b200pt_group_set_frame_counter", "b200pt_group_get_frame_counter",
+    "b200pt_group_resize", "b200pt_group_reset", "b200pt_group_set_bands", "b200pt_group_set_frame_counter", "b200pt_group_get_frame_counter",
     "b200pt_group_render_frames", "b200pt_group_synchronize", "b200pt_group_upload_target", "b200pt_group_download_target",
     "b200pt_group_render_host", "b200pt_group_resolve_ldr", "b200pt_group_get_counters", "b200pt_group_last_error",
 ]
@@ -113,6 +113,7 @@ def load_library():
                                               ctypes.POINTER(ctypes.c_uint64)]
     L.b200pt_compute_cull_rects.argtypes = [ctypes.c_int, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     L.b200pt_scale_target.argtypes = [vp, ctypes.c_float]
+    L.b200pt_scale_target_span.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, vp]
     # several GPUs of one process
     L.b200pt_group_create.argtypes = [ctypes.POINTER(Params), ctypes.POINTER(i32), i32, i32, i32, ctypes.POINTER(vp)]
     L.b200pt_group_destroy.argtypes = [vp]
@@ -122,6 +123,7 @@ def load_library():
     L.b200pt_group_set_env.argtypes = [vp, Texture]
     L.b200pt_group_resize.argtypes = [vp, i32, i32, i32, i32]
     L.b200pt_group_reset.argtypes = [vp]
+    L.b200pt_group_set_bands.argtypes = [vp, i32]
     L.b200pt_group_set_frame_counter.argtypes = [vp, i32]
     L.b200pt_group_get_frame_counter.argtypes = [vp, ctypes.POINTER(i32)]
     L.b200pt_group_render_frames.argtypes = [vp, i32]
@@ -359,6 +361,11 @@ class Renderer:
     def scale_target(self, factor):
         self._check(self._lib.b200pt_scale_target(self._ctx, ctypes.c_float(factor)), "b200pt_scale_target")
 
+    def scale_target_span(self, float_offset, float_count, factor, cuda_stream_ptr=None):
+        rc = self._lib.b200pt_scale_target_span(self._ctx, int(float_offset), int(float_count), ctypes.c_float(factor),
+                                                ctypes.c_void_p(cuda_stream_ptr))
+        self._check(rc, "b200pt_scale_target_span")
+
 
 class Group:
     """Several GPUs of this process behind one set of render entry points (b200pt_group_*): frames (SHARD_SPP) or
@@ -419,6 +426,9 @@ class Group:
 
     def reset(self):
         self._check(self._lib.b200pt_group_reset(self._g), "b200pt_group_reset")
+
+    def set_bands(self, bands):
+        self._check(self._lib.b200pt_group_set_bands(self._g, int(bands)), "b200pt_group_set_bands")
 
     @property
     def frame_counter(self):

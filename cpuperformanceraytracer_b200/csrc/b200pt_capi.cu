@@ -781,6 +781,20 @@ int b200pt_scale_target(b200pt_context* c, float factor)
     return B200PT_OK;
 }
 
+int b200pt_scale_target_span(b200pt_context* c, size_t float_offset, size_t float_count, float factor, void* cuda_stream)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    const size_t nfl = (size_t)c->width * c->height * 3;
+    if (float_offset > nfl || float_count > nfl - float_offset) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "span outside the target");
+    if (float_count == 0) return B200PT_OK;
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
+    CUDA_TRY(c, launch_scale(c->d_target + float_offset, float_count, factor, cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : c->stream));
+    c->launches++;
+    return B200PT_OK;
+}
+
 int b200pt_download_rng_state(b200pt_context* c, uint32_t* host_dst)
 {
     if (!c || !host_dst) return B200PT_ERR_INVALID_ARGUMENT;

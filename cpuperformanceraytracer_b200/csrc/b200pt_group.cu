@@ -139,6 +139,8 @@ struct b200pt_group {
     bool have_comm = false;
     bool distinct_devices = true;
     cudaEvent_t render_done[kMaxGroup] = {}, combine_done[kMaxGroup] = {};
+    cudaStream_t comm_stream[kMaxGroup] = {};  // per rank: the combine of band b runs here while band b + 1 renders
+    int bands = 0;                             // spp sharding: 0 = by buffer size (b200pt_group_set_bands)
     cudaEvent_t cb0 = nullptr, cb1 = nullptr;  // on rank 0's device: the combine step
     bool combine_timing_pending = false;
     double combine_ms = 0.0;
@@ -232,74 +234,109 @@ int record(b200pt_group* g, int r, cudaEvent_t ev)
 }
 
 // ---- B200PT_SHARD_SPP ---------------------------------------------------------------------------------------
+// The image is rendered in `bands` groups of tile rows.  A band is one contiguous span of the tile-major buffer
+// (RenderTile, ..._optimization_v4.cpp:1189-1194), so as soon as every rank has rendered band b its spans are
+// combined on the ranks' second streams while band b + 1 renders: for a large image (config 5: 805 MB of f32) the
+// exchange disappears behind the render instead of following it.
+int auto_bands(const b200pt_group* g)
+{
+    // Default: one band.  Measured on 2 B200 (config 5: 8192 x 8192, 805 MB buffer, 256 spp per GPU): the exchange after
+    // the render is 2.0 ms of 512 ms, and cutting the render into 8 launches costs more (+1.3 %) than hiding it saves.
+    // Banding pays when the render per call is short against the exchange (few frames per call on a large image).
+    if (g->bands <= 0) return 1;
+    return g->bands < g->nty ? g->bands : g->nty;
+}
+
 int render_spp(b200pt_group* g, int nframes)
 {
     const int F = g->iframe, n = g->n;
     const size_t nfl = image_floats(g);
+    const int bands = n > 1 ? auto_bands(g) : 1;
+    const size_t per_tile_row = (size_t)g->width * (size_t)(g->height / g->nty) * 3;
     // rank 0 holds the running average after F calls, A_F = (A_0 + sum of the F samples) / (F + 1) (the reference's
     // blend factor is 1/(iFrame + 1)).  A_F * (F + 1) is the sum the N new samples are added to.
     if (F > 0) GROUP_CTX(g, 0, b200pt_scale_target(g->ctx[0], (float)F + 1.f));
-    for (int r = 0; r < n; r++) {
-        size_t first, count;
-        block_of((size_t)nframes, n, r, &first, &count);
+    for (int r = 1; r < n; r++) {
         b200pt_context* c = g->ctx[r];
-        if (r > 0) {
-            DeviceGuard guard(g->device[r]);
-            GROUP_CUDA(g, guard.status);
-            GROUP_CUDA(g, cudaMemsetAsync(c->d_target, 0, nfl * sizeof(float), c->stream));
-        }
-        c->iframe = F + (int)first;
-        if (count > 0) GROUP_CTX(g, r, b200pt_render_frames(c, (int32_t)count));
-        c->iframe = F + nframes;
-        if (n > 1) {
-            const int rc = record(g, r, g->render_done[r]);
-            if (rc != B200PT_OK) return rc;
-        }
+        DeviceGuard guard(g->device[r]);
+        GROUP_CUDA(g, guard.status);
+        GROUP_CUDA(g, cudaMemsetAsync(c->d_target, 0, nfl * sizeof(float), c->stream));
     }
     const float scale = 1.0f / ((float)(F + nframes) + 1.f);  // == b200pt_finalize_sum(F + nframes)
-    {
+    for (int b = 0; b < bands; b++) {
+        const int row0 = (int)((long long)g->nty * b / bands), row1 = (int)((long long)g->nty * (b + 1) / bands);
+        const size_t off = (size_t)row0 * per_tile_row, cnt = (size_t)(row1 - row0) * per_tile_row;
+        for (int r = 0; r < n; r++) {
+            size_t first, count;
+            block_of((size_t)nframes, n, r, &first, &count);
+            b200pt_context* c = g->ctx[r];
+            c->first_tile = bands > 1 ? row0 * g->ntx : 0;
+            c->num_tiles = bands > 1 ? (row1 - row0) * g->ntx : 0;
+            c->iframe = F + (int)first;
+            if (count > 0) GROUP_CTX(g, r, b200pt_render_frames(c, (int32_t)count));
+            c->first_tile = c->num_tiles = 0;
+            c->iframe = F + nframes;
+            if (n > 1) {
+                const int rc = record(g, r, g->render_done[r]);
+                if (rc != B200PT_OK) return rc;
+            }
+        }
+        if (n == 1) continue;
+        // the band's combine, on the second streams
+        for (int r = 0; r < n; r++) {
+            DeviceGuard guard(g->device[r]);
+            GROUP_CUDA(g, guard.status);
+            if (g->combine == B200PT_COMBINE_NCCL) {
+                GROUP_CUDA(g, cudaStreamWaitEvent(g->comm_stream[r], g->render_done[r], 0));
+            } else {
+                for (int q = 0; q < n; q++) GROUP_CUDA(g, cudaStreamWaitEvent(g->comm_stream[r], g->render_done[q], 0));
+            }
+        }
+        if (g->combine == B200PT_COMBINE_NCCL) {
+            ncclResult_t nr = g_nccl.GroupStart();
+            for (int r = 0; r < n && nr == ncclSuccess; r++)
+                nr = g_nccl.Reduce(g->ctx[r]->d_target + off, g->ctx[r]->d_target + off, cnt, ncclFloat, ncclSum, 0, g->comm[r], g->comm_stream[r]);
+            const ncclResult_t ne = g_nccl.GroupEnd();
+            if (nr == ncclSuccess) nr = ne;
+            if (nr != ncclSuccess) return gfail(g, B200PT_ERR_CUDA, std::string("ncclReduce: ") + g_nccl.GetErrorString(nr));
+            DeviceGuard guard(g->device[0]);
+            GROUP_CUDA(g, guard.status);
+            GROUP_CUDA(g, launch_scale(g->ctx[0]->d_target + off, cnt, scale, g->comm_stream[0]));
+            g->launches++;
+        } else {
+            for (int r = 0; r < n; r++) {
+                PeerCombineParams pc{};
+                pc.nsrc = n;
+                for (int q = 0; q < n; q++) pc.src[q] = reinterpret_cast<const float4*>(g->ctx[q]->d_target + off);
+                pc.dst = reinterpret_cast<float4*>(g->ctx[0]->d_target + off);
+                block_of(cnt / 4, n, r, &pc.begin, &pc.count);  // a tile row holds a multiple of 24 floats
+                pc.scale = scale;
+                DeviceGuard guard(g->device[r]);
+                GROUP_CUDA(g, guard.status);
+                GROUP_CUDA(g, launch_peer_combine(pc, g->ctx[r]->sm_count, g->comm_stream[r]));
+                g->launches++;
+            }
+        }
+    }
+    {   // combine_ms = what is left of the combine after rank 0's last render launch has finished (the exposed part)
         DeviceGuard guard(g->device[0]);
         GROUP_CUDA(g, guard.status);
         GROUP_CUDA(g, cudaEventRecord(g->cb0, g->ctx[0]->stream));
     }
     if (n == 1) {
         GROUP_CTX(g, 0, b200pt_finalize_sum(g->ctx[0], F + nframes));
-    } else if (g->combine == B200PT_COMBINE_NCCL) {
-        ncclResult_t nr = g_nccl.GroupStart();
-        for (int r = 0; r < n && nr == ncclSuccess; r++)
-            nr = g_nccl.Reduce(g->ctx[r]->d_target, g->ctx[r]->d_target, nfl, ncclFloat, ncclSum, 0, g->comm[r], g->ctx[r]->stream);
-        const ncclResult_t ne = g_nccl.GroupEnd();
-        if (nr == ncclSuccess) nr = ne;
-        if (nr != ncclSuccess) return gfail(g, B200PT_ERR_CUDA, std::string("ncclReduce: ") + g_nccl.GetErrorString(nr));
-        GROUP_CTX(g, 0, b200pt_finalize_sum(g->ctx[0], F + nframes));
     } else {
-        // every rank waits for every other rank's render, combines its slice, and must not touch its SUM buffer
-        // again before every other rank's combine kernel has read it
-        for (int r = 0; r < n; r++)
-            for (int q = 0; q < n; q++)
-                if (q != r) {
-                    const int rc = stream_wait(g, r, g->render_done[q]);
-                    if (rc != B200PT_OK) return rc;
-                }
+        // every rank's next touch of its SUM buffer (and rank 0's readers) must come after every combine that reads it
         for (int r = 0; r < n; r++) {
-            PeerCombineParams pc{};
-            pc.nsrc = n;
-            for (int q = 0; q < n; q++) pc.src[q] = reinterpret_cast<const float4*>(g->ctx[q]->d_target);
-            pc.dst = reinterpret_cast<float4*>(g->ctx[0]->d_target);
-            block_of(nfl / 4, n, r, &pc.begin, &pc.count);
-            pc.scale = scale;
             DeviceGuard guard(g->device[r]);
             GROUP_CUDA(g, guard.status);
-            GROUP_CUDA(g, launch_peer_combine(pc, g->ctx[r]->sm_count, g->ctx[r]->stream));
-            g->launches++;
-            GROUP_CUDA(g, cudaEventRecord(g->combine_done[r], g->ctx[r]->stream));
+            GROUP_CUDA(g, cudaEventRecord(g->combine_done[r], g->comm_stream[r]));
         }
         for (int r = 0; r < n; r++)
-            for (int q = 0; q < n; q++)
-                if (q != r) {
-                    const int rc = stream_wait(g, r, g->combine_done[q]);
-                    if (rc != B200PT_OK) return rc;
-                }
+            for (int q = 0; q < n; q++) {
+                const int rc = stream_wait(g, r, g->combine_done[q]);
+                if (rc != B200PT_OK) return rc;
+            }
     }
     {
         DeviceGuard guard(g->device[0]);
@@ -403,7 +440,8 @@ int b200pt_group_create(const b200pt_params* params, const int32_t* devices, int
     for (int r = 0; r < g->n && rc == B200PT_OK; r++) {
         DeviceGuard guard(g->device[r]);
         if (guard.status != cudaSuccess || cudaEventCreateWithFlags(&g->render_done[r], cudaEventDisableTiming) != cudaSuccess ||
-            cudaEventCreateWithFlags(&g->combine_done[r], cudaEventDisableTiming) != cudaSuccess)
+            cudaEventCreateWithFlags(&g->combine_done[r], cudaEventDisableTiming) != cudaSuccess ||
+            cudaStreamCreateWithFlags(&g->comm_stream[r], cudaStreamNonBlocking) != cudaSuccess)
             rc = B200PT_ERR_CUDA;
         // peer access both ways: the combine kernel reads every rank's buffer and writes rank 0's
         for (int q = 0; q < g->n && rc == B200PT_OK; q++) {
@@ -457,6 +495,10 @@ int b200pt_group_destroy(b200pt_group* g)
         DeviceGuard guard(g->device[r]);
         if (g->render_done[r]) cudaEventDestroy(g->render_done[r]);
         if (g->combine_done[r]) cudaEventDestroy(g->combine_done[r]);
+        if (g->comm_stream[r]) {
+            cudaStreamSynchronize(g->comm_stream[r]);
+            cudaStreamDestroy(g->comm_stream[r]);
+        }
     }
     {
         DeviceGuard guard(g->device[0]);
@@ -493,15 +535,52 @@ int b200pt_group_resize(b200pt_group* g, int32_t width, int32_t height, int32_t 
     g->nty = nty;
     g->iframe = 0;
     if (g->sharding == B200PT_SHARD_TILES) {
+        // Contiguous flat-tile ranges (one span of the buffer per rank) of near-equal COST, not near-equal size: a tile
+        // of sky pixels (camera-culled: no scene trace) is ~10x cheaper than a tile looking into the scene, and the
+        // reference's images have the sky at the top and the scene in the middle.
+        const int ntiles = ntx * nty;
+        std::vector<double> cost((size_t)ntiles, 1.0);
+        float4 rects[kMaxCullRects];
+        const b200pt_context* c0 = g->ctx[0];
+        const int nrects = (c0->custom_scene || c0->params.disable_camera_culling) ? -1 : compute_cull_rects(c0->params.profile, width, height, rects);
+        if (nrects >= 0) {
+            const int tw = width / ntx, th = height / nty;
+            for (int t = 0; t < ntiles; t++) {
+                const int tx = t % ntx, ty = t / ntx;
+                int traced = 0, total = 0;
+                for (int ly = 0; ly < th; ly += 4)      // a 4x4 sub-sample of the tile's pixels is plenty for a weight
+                    for (int lx = 0; lx < tw; lx += 4) {
+                        const float x = (float)(tx * tw + lx), yflip = (float)(height - 1 - (ty * th + ly));
+                        bool hit = false;
+                        for (int k = 0; k < nrects; k++)
+                            if (x + 0.5f >= rects[k].x && x - 0.5f <= rects[k].z && yflip + 0.5f >= rects[k].y && yflip - 0.5f <= rects[k].w) hit = true;
+                        traced += hit ? 1 : 0;
+                        total++;
+                    }
+                cost[(size_t)t] = (double)(total - traced) + 10.0 * (double)traced;
+            }
+        }
+        double sum = 0.0;
+        for (double v : cost) sum += v;
+        int t = 0;
+        double acc = 0.0;
         for (int r = 0; r < g->n; r++) {
-            size_t first, count;
-            block_of((size_t)ntx * nty, g->n, r, &first, &count);
-            g->tile_first[r] = (int)first;
-            g->tile_count[r] = (int)count;
+            const double target = sum * (double)(r + 1) / (double)g->n;
+            const int first = t;
+            while (t < ntiles && (r == g->n - 1 || acc + 0.5 * cost[(size_t)t] <= target)) acc += cost[(size_t)t++];
+            g->tile_first[r] = first;
+            g->tile_count[r] = t - first;
             // (0, 0) would mean "all tiles": a rank without tiles simply never launches
-            if (count > 0) GROUP_CTX(g, r, b200pt_set_tile_range(g->ctx[r], (int32_t)first, (int32_t)count));
+            if (t > first) GROUP_CTX(g, r, b200pt_set_tile_range(g->ctx[r], (int32_t)first, (int32_t)(t - first)));
         }
     }
+    return B200PT_OK;
+}
+
+int b200pt_group_set_bands(b200pt_group* g, int32_t bands)
+{
+    if (!g || bands < 0) return B200PT_ERR_INVALID_ARGUMENT;
+    g->bands = bands;
     return B200PT_OK;
 }
 

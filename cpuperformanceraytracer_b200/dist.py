@@ -42,15 +42,47 @@ class TileRowShard:
     float_count: int
 
 
-def shard_tile_rows(width: int, height: int, num_tiles_y: int, world_size: int, rank: int) -> TileRowShard:
-    """Tile-row bands: one contiguous span of the band-major buffer per rank."""
+def shard_tile_rows(width: int, height: int, num_tiles_y: int, world_size: int, rank: int, row_costs=None) -> TileRowShard:
+    """Tile-row bands: one contiguous span of the band-major buffer per rank.  row_costs (one weight per tile row)
+    makes the bands near-equal in COST instead of near-equal in rows: sky rows are ~10x cheaper than scene rows."""
     if height % num_tiles_y or world_size <= 0 or not (0 <= rank < world_size):
         raise ValueError("bad shard request")
-    base, rem = divmod(num_tiles_y, world_size)
-    n = base + (1 if rank < rem else 0)
-    start = rank * base + min(rank, rem)
     band = (height // num_tiles_y) * width * 3
+    if row_costs is None:
+        base, rem = divmod(num_tiles_y, world_size)
+        n = base + (1 if rank < rem else 0)
+        start = rank * base + min(rank, rem)
+        return TileRowShard(start, n, start * band, n * band)
+    if len(row_costs) != num_tiles_y or min(row_costs) < 0:
+        raise ValueError("one non-negative cost per tile row")
+    total = float(sum(row_costs))
+    t, acc, bounds = 0, 0.0, [0]
+    for r in range(world_size):
+        target = total * (r + 1) / world_size
+        while t < num_tiles_y and (r == world_size - 1 or acc + 0.5 * row_costs[t] <= target):
+            acc += row_costs[t]
+            t += 1
+        bounds.append(t)
+    start, n = bounds[rank], bounds[rank + 1] - bounds[rank]
     return TileRowShard(start, n, start * band, n * band)
+
+
+def tile_row_costs(cull_rects, width: int, height: int, num_tiles_y: int, traced_weight: float = 10.0):
+    """Relative cost of every tile row from the camera-culling rectangles (api.cull_rects): a pixel whose jitter footprint
+    touches no rectangle never traces the scene (weight 1), the others do (weight traced_weight)."""
+    import numpy as np
+    th = height // num_tiles_y
+    if cull_rects is None:
+        return [1.0] * num_tiles_y
+    xs = np.arange(0, width, 4, dtype=np.float32)[None, :]
+    costs = []
+    for ty in range(num_tiles_y):
+        ys = (height - 1 - np.arange(ty * th, (ty + 1) * th, 4, dtype=np.float32))[:, None]  # flipped rows, like fragCoord.y
+        hit = np.zeros((ys.shape[0], xs.shape[1]), dtype=bool)
+        for (x0, y0, x1, y1) in np.asarray(cull_rects, dtype=np.float32).reshape(-1, 4):
+            hit |= (xs + 0.5 >= x0) & (xs - 0.5 <= x1) & (ys + 0.5 >= y0) & (ys - 0.5 <= y1)
+        costs.append(float((~hit).sum() + traced_weight * hit.sum()))
+    return costs
 
 
 def finalize_scale(last_frame: int) -> float:
@@ -77,6 +109,8 @@ class SppShardedRenderer:
         from . import api
         self.torch = torch
         self.rank, self.world = rank, world_size
+        self.width, self.height, self.nty = width, height, nty
+        self.comm_stream = None
         self.device = torch.device("cuda", device)
         self.r = renderer_factory(accum_mode=api.ACCUM_SUM, device=device)
         self.r.resize(width, height, ntx, nty)
@@ -87,27 +121,55 @@ class SppShardedRenderer:
         self.r.set_stream(self.stream.cuda_stream)
         torch.cuda.synchronize(self.device)
 
-    def render(self, total_frames, first_frame=1, resume=False):
+    def render(self, total_frames, first_frame=1, resume=False, bands=1):
         """Renders frames [first_frame, first_frame + total_frames) of the job, sharded over the ranks, reduces, scales.
         Asynchronous.  resume=False: a fresh job (first_frame must be 1): every rank zeroes its SUM buffer.
         resume=True: rank 0's buffer holds the running average after first_frame - 1 render calls (any caller state
         for first_frame = 1); it is turned back into a sum, A * first_frame (the reference's blend factor is
         1/(iFrame + 1)), the other ranks start from zero, and the result is the reference's average
-        after first_frame - 1 + total_frames calls."""
+        after first_frame - 1 + total_frames calls.
+        bands > 1: the image is rendered in `bands` groups of tile rows; a band is one contiguous span of the
+        tile-major buffer, and its all-reduce + scale run on a second stream while the next band renders, so the
+        exchange of a large image (8192 x 8192: 805 MB) hides behind the render."""
         if first_frame < 1 or (first_frame != 1 and not resume):
             raise ValueError("a fresh job starts at frame 1; pass resume=True to continue from rank 0's buffer")
+        torch = self.torch
         sh = shard_frames(total_frames, self.world, self.rank, first_frame)
-        with self.torch.cuda.stream(self.stream):
+        last = first_frame - 1 + total_frames
+        bands = max(1, min(int(bands), self.nty))
+        with torch.cuda.stream(self.stream):
             if resume and self.rank == 0:
                 if first_frame > 1:
                     self.r.scale_target(float(first_frame))
             else:
                 self.buf.zero_()
-            self.r.frame_counter = sh.first_frame - 1
-            self.r.render_frames(sh.nframes, sync=False)
-            reduce_sum_(self.buf)
-            self.r.finalize_sum(first_frame - 1 + total_frames)
-            self.r.frame_counter = first_frame - 1 + total_frames
+        if bands == 1:
+            with torch.cuda.stream(self.stream):
+                self.r.frame_counter = sh.first_frame - 1
+                self.r.render_frames(sh.nframes, sync=False)
+                reduce_sum_(self.buf)
+                self.r.finalize_sum(last)
+        else:
+            if self.comm_stream is None:
+                self.comm_stream = torch.cuda.Stream(self.device)
+            per_row = self.width * (self.height // self.nty) * 3
+            scale = finalize_scale(last)
+            for b in range(bands):
+                row0, row1 = self.nty * b // bands, self.nty * (b + 1) // bands
+                with torch.cuda.stream(self.stream):
+                    self.r.set_tile_row_range(row0, row1 - row0)
+                    self.r.frame_counter = sh.first_frame - 1
+                    self.r.render_frames(sh.nframes, sync=False)
+                    done = torch.cuda.Event()
+                    done.record(self.stream)
+                self.comm_stream.wait_event(done)
+                with torch.cuda.stream(self.comm_stream):
+                    off, cnt = row0 * per_row, (row1 - row0) * per_row
+                    reduce_sum_(self.buf[off:off + cnt])
+                    self.r.scale_target_span(off, cnt, scale, self.comm_stream.cuda_stream)
+            self.r.set_tile_row_range(0, 0)  # back to the whole image
+            self.stream.wait_stream(self.comm_stream)
+        self.r.frame_counter = last
         return self.buf
 
     def close(self):
@@ -125,8 +187,11 @@ class TileShardedRenderer:
         self.torch = torch
         self.rank, self.world = rank, world_size
         self.device = torch.device("cuda", device)
-        self.shards = [shard_tile_rows(width, height, nty, world_size, r) for r in range(world_size)]
         self.r = renderer_factory(accum_mode=api.ACCUM_RUNNING_AVERAGE, device=device)
+        costs = None
+        if not self.r.params.disable_camera_culling:
+            costs = tile_row_costs(api.cull_rects(self.r.params.profile, width, height), width, height, nty)
+        self.shards = [shard_tile_rows(width, height, nty, world_size, r, costs) for r in range(world_size)]
         self.r.resize(width, height, ntx, nty)
         self.buf = torch.zeros(width * height * 3, dtype=torch.float32, device=self.device)
         self.r.bind_device_target(self.buf.data_ptr())

@@ -234,6 +234,9 @@ int b200pt_finalize_sum(b200pt_context* ctx, int32_t total_frames);
 /* target *= factor on the context's stream (ACCUM_SUM prologue of a continued job: a buffer holding the
  * running average after F frames, times (F + 1), is the sum of those F samples) */
 int b200pt_scale_target(b200pt_context* ctx, float factor);
+/* the same on floats [float_offset, float_offset + float_count) of the target, on `cuda_stream` (NULL = the
+ * context's stream): the epilogue of ONE band of a band-pipelined spp-sharded render */
+int b200pt_scale_target_span(b200pt_context* ctx, size_t float_offset, size_t float_count, float factor, void* cuda_stream);
 
 /* ---- several GPUs of one box behind the same entry points ------------------------------------------
  * The reference fans one render call out to its worker threads below the entry point
@@ -268,6 +271,11 @@ b200pt_context* b200pt_group_context(b200pt_group* group, int32_t rank);
 int b200pt_group_set_env(b200pt_group* group, b200pt_texture tex);
 int b200pt_group_resize(b200pt_group* group, int32_t width, int32_t height, int32_t num_tiles_x, int32_t num_tiles_y);
 int b200pt_group_reset(b200pt_group* group);
+/* B200PT_SHARD_SPP: the image is rendered in `bands` groups of tile rows and the combine of band b (one contiguous
+ * span of the buffer) runs on second streams while band b + 1 renders, so the exchange of a large image hides behind
+ * the render.  0 (default) = 1 band: with hundreds of frames per call the exchange is < 1 % of the call even for an
+ * 8192 x 8192 image; banding pays for short calls on large images. */
+int b200pt_group_set_bands(b200pt_group* group, int32_t bands);
 int b200pt_group_set_frame_counter(b200pt_group* group, int32_t iframe);
 int b200pt_group_get_frame_counter(b200pt_group* group, int32_t* iframe);
 /* == nframes consecutive render calls of the reference, sharded; asynchronous; the image lives on rank 0 */
@@ -282,7 +290,8 @@ int b200pt_group_render_host(b200pt_group* group, float* BufferOut, int32_t Buff
 /* CopyOutputToFile on rank 0's image */
 int b200pt_group_resolve_ldr(b200pt_group* group, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter);
 /* counters summed over the ranks; last_render_ms = the longest rank's last launch; *combine_ms (may be NULL) =
- * device time of the last combine step (reduce + scale, or span copies) on rank 0's stream */
+ * device time between the end of rank 0's last render launch and the end of the combine (reduce + scale, or span
+ * copies): the part of the exchange that is NOT hidden behind rendering (it includes waiting for slower ranks) */
 int b200pt_group_get_counters(b200pt_group* group, b200pt_counters* out, double* combine_ms);
 const char* b200pt_group_last_error(b200pt_group* group);
 

@@ -5,6 +5,9 @@ one JSON line each.  Run under torchrun for N > 1:  python -m torch.distributed.
     --config 3   simt_textured (and P_v4 equirect) 3840x2160, spp-sharded, synthetic 2048x1024 env
     --config 4   P_v4 + cubemap, 1080p progressive 1 spp/frame: per-frame latency (render + tone map + D2H)
     --config 5   8192x8192, 16 bounces, strong scaling: spp-shard reduce vs tile-shard gather
+Every line carries cpu_baseline: the reference's own renderer of that configuration (oracle/_ref/ref_*_asis) on all host
+cores, on a bounded sample (--no-cpu-baseline skips it).
+    --group N    configs 3 / 5 in ONE process through the C ABI's b200pt_group_* (no torch.distributed): N GPUs
 """
 import argparse, json, os, sys, time
 import numpy as np
@@ -17,6 +20,8 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", type=int, required=True)
 ap.add_argument("--spp", type=int, default=0)
 ap.add_argument("--math", default="parity")
+ap.add_argument("--group", type=int, default=0)
+ap.add_argument("--no-cpu-baseline", action="store_true")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
 torch.cuda.set_device(local)
@@ -29,7 +34,7 @@ MATH = api.MATH_PARITY if args.math == "parity" else api.MATH_FAST
 
 def out(d):
     if rank == 0:
-        d.update(n_gpus=world, math=args.math)
+        d.update(n_gpus=d.pop("n_gpus_group", world), math=args.math)
         print(json.dumps(d), flush=True)
 
 
@@ -37,6 +42,30 @@ def sync():
     if world > 1:
         tdist.barrier()
     torch.cuda.synchronize(dev)
+
+
+def cpu_baseline(binary, W, H, ntx, nty, frames, bounces, env=None, threads=None):
+    """the reference's own renderer (asis build) on the host, bounded sample; rank 0 only"""
+    if rank != 0 or args.no_cpu_baseline:
+        return None
+    from oracle import pyoracle as po
+    ncores = os.cpu_count() or 1
+    if not po.ref_binary(binary):
+        return {"kind": "unavailable", "sample": binary + " not built"}
+    th = threads or ncores
+    try:
+        t = po.run_ref(binary, W, H, ntx, nty, frames, bounces=bounces, env=env, threads=th, time_it=True, warmup=1)["timing"]
+    except Exception as e:
+        return {"kind": "unavailable", "sample": str(e)[:200]}
+    return {"value": t["mpaths_per_s"], "unit": "Mpaths/s", "cores": min(th, ncores), "host_cores": ncores, "kind": "reference",
+            "sample": f"{binary}, {W}x{H}, tiles {ntx}x{nty}, {th} threads, 1 warm-up + {frames} timed frames, {t['seconds']:.2f} s"}
+
+
+def timed_group(G, fn):
+    """device time of fn() on a b200pt group: wall clock around fn + synchronize, after a warm-up call"""
+    fn(); G.synchronize()
+    t0 = time.perf_counter(); fn(); G.synchronize()
+    return (time.perf_counter() - t0) * 1e3
 
 
 if args.config == 1:
@@ -48,6 +77,7 @@ if args.config == 1:
         g = r.download_target(); c = r.counters(); rs = r.rng_state()
     d = np.abs(g.astype(np.float64) - o)
     out({"config": 1, "workload": "Cornell P_v2 512x512 tiles 2x4, 64 spp, 8 bounces", "gpu_ms": c["last_render_ms"],
+         "cpu_baseline": cpu_baseline("ref_v2_asis", W, H, 2, 4, 64, 8, threads=8),
          "mpaths_per_s": W * H * 64 / c["last_render_ms"] * 1e-3, "bit_exact_vs_oracle": bool(np.array_equal(g, o)),
          "rmse": float(np.sqrt((d ** 2).mean())), "max_abs": float(d.max()), "oracle_port_seconds": tcpu,
          "segments_match": bool(c["segments"] % (2 ** 64) >= oc["segments"])})
@@ -56,9 +86,28 @@ elif args.config == 3:
     W, H, ntx, nty = 3840, 2160, 10, 15
     spp = args.spp or 256
     env = po.synthetic_env(2048, 1024)
-    for name, prof, kw in (("simt_textured", api.PROFILE_SIMT_TEXTURED, {}),
-                           ("v4_equirect_random", api.PROFILE_OPT_V4, dict(env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM))):
+    for name, prof, kw, refbin in (("simt_textured", api.PROFILE_SIMT_TEXTURED, {}, "ref_simt_textured_asis"),
+                                   ("v4_equirect_random", api.PROFILE_OPT_V4, dict(env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM),
+                                    "ref_v4_equirect_random_asis")):
         bounces = 4 if prof == api.PROFILE_SIMT_TEXTURED else 8
+        # simt_textured keeps the v2 renderer's 8-tile table (simt_textured.cpp WorkData[8]): tiles 2x4, 8 threads
+        base = cpu_baseline(refbin, W, H, 2 if refbin.startswith("ref_simt") else ntx, 4 if refbin.startswith("ref_simt") else nty,
+                            4 if refbin.startswith("ref_simt") else 16, bounces, env=env, threads=8 if refbin.startswith("ref_simt") else None)
+        if args.group:
+            n = args.group
+            for sharding, combine, label in ((api.SHARD_SPP, api.COMBINE_NCCL, "spp-shard, NCCL reduce"),
+                                             (api.SHARD_SPP, api.COMBINE_PEER, "spp-shard, peer-memory combine kernel"),
+                                             (api.SHARD_TILES, api.COMBINE_PEER, "tile-shard, span copies")):
+                with api.Group(list(range(n)), sharding=sharding, combine=combine, profile=prof, math_mode=MATH, num_bounces=bounces, **kw) as G:
+                    G.set_env(env); G.resize(W, H, ntx, nty)
+                    def job():
+                        G.reset(); G.render_frames(spp * n, sync=False)
+                    ms = timed_group(G, job)
+                    c = G.counters()
+                out({"config": 3, "profile": name, "api": "b200pt_group_* (one process, C ABI)", "sharding": label, "n_gpus_group": n,
+                     "workload": f"{W}x{H}, {spp} spp per GPU (bounded sample of 4096), synthetic 2048x1024 equirect env",
+                     "ms": ms, "mpaths_per_s": W * H * spp * n / ms * 1e-3, "exposed_combine_ms": c["combine_ms"], "cpu_baseline": base})
+            continue
         def factory(accum_mode=api.ACCUM_RUNNING_AVERAGE, device=local):
             r = api.Renderer(profile=prof, math_mode=MATH, num_bounces=bounces, device=device, accum_mode=accum_mode, **kw)
             r.set_env(env)
@@ -72,7 +121,7 @@ elif args.config == 3:
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
         if world > 1: tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
         out({"config": 3, "profile": name, "workload": f"{W}x{H}, {spp} spp per GPU (bounded sample of 4096), synthetic 2048x1024 equirect env, spp-shard + all-reduce",
-             "ms": float(ms), "mpaths_per_s": W * H * spp * world / float(ms) * 1e-3})
+             "ms": float(ms), "mpaths_per_s": W * H * spp * world / float(ms) * 1e-3, "cpu_baseline": base})
         sr.close()
 elif args.config == 4:
     from oracle import pyoracle as po
@@ -112,7 +161,9 @@ elif args.config == 4:
         for f in range(frames):
             r.present_submit(1); r.present_acquire(copy=False)
         ring_ms = (time.perf_counter() - t0) * 1e3 / frames
-    out({"config": 4, "workload": "P_v4 + cubemap 512x3072 atlas, 1920x1080 progressive, 1 spp/frame, 600 frames",
+    base = cpu_baseline("ref_v4_cubemap_random_asis", W, H, ntx, nty, 16, 8, env=cube)
+    out({"config": 4, "workload": "P_v4 + cubemap 512x3072 atlas, 1920x1080 progressive, 1 spp/frame, 600 frames", "cpu_baseline": base,
+         "cpu_ms_per_frame": (W * H / (base["value"] * 1e3)) if base and base.get("value") else None,
          "latency_ms_p50": float(np.percentile(lat, 50)), "latency_ms_p95": float(np.percentile(lat, 95)),
          "latency_ms_mean": float(lat.mean()), "kernel_ms_last": c["last_render_ms"], "present_ring_ms_per_frame": ring_ms,
          "present_ring_fps": 1e3 / ring_ms, "present_blocking_latency_ms_by_bands": blocking,
@@ -120,29 +171,49 @@ elif args.config == 4:
 elif args.config == 5:
     W = H = 8192
     ntx, nty = 16, 64
-    total = args.spp or 64  # bounded sample of the 16384-spp job; strong scaling: total fixed
-    def factory(accum_mode=api.ACCUM_RUNNING_AVERAGE, device=local):
-        return api.Renderer(profile=api.PROFILE_V2, math_mode=MATH, num_bounces=16, device=device, accum_mode=accum_mode)
-    for mode in ("spp-shard reduce", "tile-shard gather"):
-        R = ptdist.SppShardedRenderer(factory, W, H, ntx, nty, rank, world, local) if mode.startswith("spp") else \
-            ptdist.TileShardedRenderer(factory, W, H, ntx, nty, rank, world, local)
-        def step():
-            if mode.startswith("spp"):
-                R.render(total)
-            else:
-                with torch.cuda.stream(R.stream):
-                    R.buf.zero_()
-                R.r.frame_counter = 0
-                R.render(total)
-        step(); R.stream.synchronize(); sync()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        with torch.cuda.stream(R.stream):
-            e0.record(R.stream); step(); e1.record(R.stream)
-        sync()
-        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
-        if world > 1: tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
-        out({"config": 5, "sharding": mode, "workload": f"Cornell P_v2 {W}x{H}, {total} spp total (bounded sample of 16384), 16 bounces, strong scaling",
-             "ms": float(ms), "mpaths_per_s": W * H * total / float(ms) * 1e-3})
-        R.close()
+    total = args.spp or 512  # bounded sample of the 16384-spp job; strong scaling: total fixed whatever the GPU count
+    base = cpu_baseline("ref_v2_asis", 2048, 2048, 2, 4, 2, 16, threads=8)  # a 2048^2 crop-sized image: throughput is size-independent
+    wl = f"Cornell P_v2 {W}x{H}, {total} spp total (bounded sample of 16384), 16 bounces, strong scaling"
+    if args.group:
+        n = args.group
+        for sharding, combine, bands, label in ((api.SHARD_SPP, api.COMBINE_NCCL, 1, "spp-shard, NCCL reduce after the render"),
+                                                (api.SHARD_SPP, api.COMBINE_NCCL, 0, "spp-shard, NCCL reduce per band behind the render"),
+                                                (api.SHARD_SPP, api.COMBINE_PEER, 1, "spp-shard, peer-memory combine kernel after the render"),
+                                                (api.SHARD_SPP, api.COMBINE_PEER, 0, "spp-shard, peer-memory combine kernel per band behind the render"),
+                                                (api.SHARD_TILES, api.COMBINE_PEER, 1, "tile-shard, span copies")):
+            with api.Group(list(range(n)), sharding=sharding, combine=combine, profile=api.PROFILE_V2, math_mode=MATH, num_bounces=16) as G:
+                G.resize(W, H, ntx, nty)
+                G.set_bands(bands)
+                def job():
+                    G.reset(); G.render_frames(total, sync=False)
+                ms = timed_group(G, job)
+                c = G.counters()
+            out({"config": 5, "api": "b200pt_group_* (one process, C ABI)", "sharding": label, "n_gpus_group": n, "workload": wl,
+                 "ms": ms, "mpaths_per_s": W * H * total / ms * 1e-3, "exposed_combine_ms": c["combine_ms"], "cpu_baseline": base})
+    else:
+        def factory(accum_mode=api.ACCUM_RUNNING_AVERAGE, device=local):
+            return api.Renderer(profile=api.PROFILE_V2, math_mode=MATH, num_bounces=16, device=device, accum_mode=accum_mode)
+        for mode, bands in (("spp-shard, all-reduce after the render", 1), ("spp-shard, all-reduce per band behind the render", 8),
+                            ("tile-shard gather", 1)):
+            R = ptdist.SppShardedRenderer(factory, W, H, ntx, nty, rank, world, local) if mode.startswith("spp") else \
+                ptdist.TileShardedRenderer(factory, W, H, ntx, nty, rank, world, local)
+            def step():
+                if mode.startswith("spp"):
+                    R.render(total, bands=bands)
+                else:
+                    with torch.cuda.stream(R.stream):
+                        R.buf.zero_()
+                    R.r.frame_counter = 0
+                    R.render(total)
+            step(); R.stream.synchronize(); sync()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            with torch.cuda.stream(R.stream):
+                e0.record(R.stream); step(); e1.record(R.stream)
+            sync()
+            ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+            if world > 1: tdist.all_reduce(ms, op=tdist.ReduceOp.MAX)
+            out({"config": 5, "sharding": mode, "workload": wl, "ms": float(ms), "mpaths_per_s": W * H * total / float(ms) * 1e-3,
+                 "cpu_baseline": base})
+            R.close()
 if world > 1:
     tdist.barrier(); tdist.destroy_process_group()

@@ -86,3 +86,30 @@ def test_gloo_world2_spp_reduce_and_tile_gather(tmp_path):
     assert np.allclose(a, seq, rtol=1e-6, atol=1e-7)
     t0, t1 = np.load(tmp_path / "tile_0.npy"), np.load(tmp_path / "tile_1.npy")
     assert np.array_equal(t0, np.arange(16 * 8 * 3, dtype=np.float32)) and np.array_equal(t0, t1)
+
+
+def test_cost_weighted_tile_rows_cover_the_image_once():
+    """cost-balanced bands: contiguous, disjoint, complete; a cheap sky above an expensive scene moves the cut down"""
+    costs = [1.0] * 6 + [10.0] * 6
+    for world in (1, 2, 3, 5, 12, 16):
+        rows, total = [], 0
+        for r in range(world):
+            sh = ptdist.shard_tile_rows(96, 120, 12, world, r, costs)
+            rows += list(range(sh.first_tile_row, sh.first_tile_row + sh.num_tile_rows))
+            assert sh.float_offset == sh.first_tile_row * 10 * 96 * 3 and sh.float_count == sh.num_tile_rows * 10 * 96 * 3
+            total += sh.num_tile_rows
+        assert rows == list(range(12)) and total == 12
+    a, b = (ptdist.shard_tile_rows(96, 120, 12, 2, r, costs) for r in (0, 1))
+    assert a.num_tile_rows > b.num_tile_rows  # 6 sky rows + some scene rows against the rest of the scene rows
+    per_rank = [sum(costs[s.first_tile_row:s.first_tile_row + s.num_tile_rows]) for s in (a, b)]
+    assert max(per_rank) <= 0.6 * sum(costs)
+    import pytest
+    with pytest.raises(ValueError):
+        ptdist.shard_tile_rows(96, 120, 12, 2, 0, [1.0] * 5)
+
+
+def test_tile_row_costs_from_cull_rects():
+    rects = [(10.0, 20.0, 50.0, 60.0)]  # fragCoord space, y flipped: image rows 59 .. 99 of a 120-row image
+    c = ptdist.tile_row_costs(rects, 96, 120, 12)
+    assert len(c) == 12 and c[0] == c[1] == min(c) and max(c) == c[7] and c[11] == min(c)
+    assert ptdist.tile_row_costs(None, 96, 120, 12) == [1.0] * 12

@@ -91,8 +91,15 @@ def test_spp_shard_group_peer_combine(label, devices):
         g.reset()
         g.render_frames(24)
         assert np.array_equal(g.download_target(), a)
+        # band-pipelined: the combine of a band of tile rows runs while the next band renders -- same sums, same order
+        for bands in (2, 4, 9):
+            g.set_bands(bands)
+            g.reset()
+            g.render_frames(24)
+            assert np.array_equal(g.download_target(), a), bands
+        g.set_bands(0)
         c = g.counters()
-        assert c["paths"] == W * H * (24 + 9 + 24) and c["combine_ms"] > 0.0
+        assert c["paths"] == W * H * (24 + 9 + 24 + 3 * 24) and c["combine_ms"] > 0.0
         # fewer frames than ranks: some ranks render nothing
         g.reset()
         g.render_frames(2)
@@ -135,6 +142,10 @@ def test_spp_shard_group_nccl():
         assert np.allclose(g.download_target(), seq[0], rtol=3e-6, atol=3e-6)
         g.render_frames(9)
         assert np.allclose(g.download_target(), seq[1], rtol=3e-6, atol=3e-6)
+        g.set_bands(3)  # NCCL reduce per band on the second streams
+        g.reset()
+        g.render_frames(24)
+        assert np.allclose(g.download_target(), seq[0], rtol=3e-6, atol=3e-6)
 
 
 def test_group_argument_checking():

@@ -34,6 +34,13 @@ sr = ptdist.SppShardedRenderer(factory, W, H, ntx, nty, rank, world, local)
 buf = sr.render(total)
 sr.stream.synchronize()
 out = buf.cpu().numpy()
+buf = sr.render(total, bands=3)   # all-reduce per band of tile rows, overlapped with the next band's render
+sr.stream.synchronize()
+banded = buf.cpu().numpy()
+# continued job: 10 more frames on top of the reduced image (rank 0's buffer holds the average after `total` calls)
+buf = sr.render(10, first_frame=total + 1, resume=True)
+sr.stream.synchronize()
+cont = buf.cpu().numpy()
 tr = ptdist.TileShardedRenderer(factory, W, H, ntx, nty, rank, world, local)
 tbuf = tr.render(total)
 tr.stream.synchronize()
@@ -41,7 +48,8 @@ tout = tbuf.cpu().numpy()
 if rank == 0:
     with factory() as r:
         r.resize(W, H, ntx, nty); r.render_frames(total); seq = r.download_target()
-    np.save(sys.argv[1], np.stack([out, seq, tout]))
+        r.render_frames(10); seq2 = r.download_target()
+    np.save(sys.argv[1], np.stack([out, seq, tout, banded, cont, seq2]))
 tdist.barrier(); tdist.destroy_process_group()
 '''
 
@@ -54,8 +62,12 @@ def test_spp_shard_matches_sequential(tmp_path):
     n = min(_ngpus(), 4)
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}", "--master-addr",
                     "127.0.0.1", "--master-port", "29541", str(script), str(out)], check=True, timeout=600)
-    sharded, seq, tiled = np.load(out)
+    sharded, seq, tiled, banded, cont, seq2 = np.load(out)
     # same samples, different summation order (sum then scale vs running average): ~1e-6 relative
     assert np.allclose(sharded, seq, rtol=3e-6, atol=3e-6)
     # tile-shard: bit-identical to the single-GPU render
     assert np.array_equal(tiled, seq)
+    # band-pipelined exchange: the same sums (NCCL may pick another reduction order per message size: tolerance, not bits)
+    assert np.allclose(banded, seq, rtol=3e-6, atol=3e-6)
+    # resume=True continues the job from the reduced image
+    assert np.allclose(cont, seq2, rtol=3e-6, atol=3e-6)
