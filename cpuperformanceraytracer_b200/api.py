@@ -51,7 +51,7 @@ class Params(ctypes.Structure):
                 ("math_mode", ctypes.c_int32), ("num_bounces", ctypes.c_int32), ("env_kind", ctypes.c_int32),
                 ("env_sampler", ctypes.c_int32), ("accum_mode", ctypes.c_int32), ("output_to_screen", ctypes.c_int32),
                 ("disable_camera_culling", ctypes.c_int32), ("generic_scene_tables", ctypes.c_int32),
-                ("scheduler", ctypes.c_int32), ("reserved", ctypes.c_int32 * 4)]
+                ("scheduler", ctypes.c_int32), ("disable_item_order", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3)]
 
 
 class Counters(ctypes.Structure):
@@ -157,7 +157,7 @@ class Renderer:
 
     def __init__(self, profile=PROFILE_V2, math_mode=MATH_PARITY, num_bounces=-1, device=0, env_kind=None,
                  env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False,
-                 disable_camera_culling=False, generic_scene_tables=False, scheduler=SCHED_DEFAULT):
+                 disable_camera_culling=False, generic_scene_tables=False, scheduler=SCHED_DEFAULT, disable_item_order=False):
         self._lib = load_library()
         self._ctx = ctypes.c_void_p()
         p = default_params(profile)
@@ -166,6 +166,7 @@ class Renderer:
         p.disable_camera_culling = int(bool(disable_camera_culling))
         p.generic_scene_tables = int(bool(generic_scene_tables))
         p.scheduler = int(scheduler)
+        p.disable_item_order = int(bool(disable_item_order))
         if env_kind is not None:
             p.env_kind = env_kind
         if env_sampler is not None:

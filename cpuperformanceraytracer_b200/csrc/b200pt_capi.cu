@@ -106,6 +106,89 @@ int collect_timing(b200pt_context* c, bool wait)
     return B200PT_OK;
 }
 
+// The pull order of a launch's work items (RenderParams::item_order).  Items are pulled from one atomic counter; an
+// item that looks into the scene costs ~15x a sky-only one (camera-culled pixels never trace), so pulling the
+// expensive ones first leaves the cheap ones to even out the end of the launch -- what the reference gets from its
+// fine-grained per-tile queue (work_queue.cpp:7-66).  Classification: the item's pixel block against the culling
+// rectangles (conservative; the kernel still decides per pixel).  Returns 0 on success.
+int ensure_item_order(b200pt_context* c, const RenderParams& rp)
+{
+    if (rp.num_cull_rects <= 0 || c->params.disable_item_order || rp.num_items < 2 * c->sm_count * 8) {
+        c->item_order_key = 0;
+        return B200PT_OK;  // nothing to gain: launch without an order table
+    }
+    unsigned long long key = 1469598103934665603ull;
+    auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
+    mix((unsigned)rp.width); mix((unsigned)rp.height); mix((unsigned)rp.tile_w); mix((unsigned)rp.tile_h); mix((unsigned)rp.num_tiles_x);
+    mix((unsigned)rp.group_offset); mix((unsigned)rp.num_groups); mix((unsigned)rp.block_items); mix((unsigned)rp.num_cull_rects);
+    for (int k = 0; k < rp.num_cull_rects; k++) {
+        unsigned u[4];
+        std::memcpy(u, &rp.cull_rect[k], sizeof(u));
+        for (unsigned w : u) mix(w);
+    }
+    if (key == 0) key = 1;
+    if (key == c->item_order_key && c->d_item_order) return B200PT_OK;
+    // Build the table only for a geometry that is launched twice in a row: callers that walk over tile ranges (bands
+    // of a pipelined present, per-tile scheduling) change it on every launch and must not pay a rebuild + sync each time.
+    if (key != c->item_order_candidate) {
+        c->item_order_candidate = key;
+        c->item_order_key = 0;
+        return B200PT_OK;
+    }
+    std::vector<int> traced, sky;
+    traced.reserve((size_t)rp.num_items);
+    const int per_tile = rp.groups_per_tile >> 2;
+    for (int item = 0; item < rp.num_items; item++) {
+        // pixel bounds of the item: an 8x4 block, or 4 consecutive groups of a tile row (pt_render_kernel's mapping)
+        int x0, x1, y0, y1;
+        if (rp.block_items) {
+            const int t = item / per_tile, it = item - t * per_tile;
+            const int band = it / rp.groups_per_tile_row, gx = it - band * rp.groups_per_tile_row;
+            const int g = rp.group_offset + t * rp.groups_per_tile + band * 4 * rp.groups_per_tile_row + gx;
+            const int tile = g / rp.groups_per_tile, r = g - tile * rp.groups_per_tile;
+            const int ty = tile / rp.num_tiles_x, tx = tile - ty * rp.num_tiles_x;
+            const int ly = r / rp.groups_per_tile_row, gxx = r - ly * rp.groups_per_tile_row;
+            x0 = tx * rp.tile_w + gxx * 8; x1 = x0 + 7;
+            y0 = ty * rp.tile_h + ly; y1 = y0 + 3;
+        } else {
+            const int g0 = rp.group_offset + item * 4;
+            int gl1 = item * 4 + 3;
+            if (gl1 >= rp.num_groups) gl1 = rp.num_groups - 1;
+            const int g1 = rp.group_offset + gl1;
+            auto pix = [&](int g, int& x, int& y) {
+                const int tile = g / rp.groups_per_tile, r = g - tile * rp.groups_per_tile;
+                const int ty = tile / rp.num_tiles_x, tx = tile - ty * rp.num_tiles_x;
+                const int ly = r / rp.groups_per_tile_row, gxx = r - ly * rp.groups_per_tile_row;
+                x = tx * rp.tile_w + gxx * 8; y = ty * rp.tile_h + ly;
+            };
+            int xa, ya, xb, yb;
+            pix(g0, xa, ya); pix(g1, xb, yb);
+            if (ya == yb) { x0 = xa; x1 = xb + 7; y0 = y1 = ya; }
+            else { x0 = 0; x1 = rp.width - 1; y0 = ya < yb ? ya : yb; y1 = ya < yb ? yb : ya; }  // wraps a row / a tile: be conservative
+        }
+        const float fx0 = (float)x0 - 0.5f, fx1 = (float)x1 + 0.5f;
+        const float fy0 = (float)(rp.height - 1 - y1) - 0.5f, fy1 = (float)(rp.height - 1 - y0) + 0.5f;  // flipped rows
+        bool hit = false;
+        for (int k = 0; k < rp.num_cull_rects && !hit; k++)
+            hit = fx1 >= rp.cull_rect[k].x && fx0 <= rp.cull_rect[k].z && fy1 >= rp.cull_rect[k].y && fy0 <= rp.cull_rect[k].w;
+        (hit ? traced : sky).push_back(item);
+    }
+    c->item_order_traced = (int)traced.size();
+    traced.insert(traced.end(), sky.begin(), sky.end());
+    if (c->item_order_capacity < traced.size()) {
+        if (c->d_item_order) cudaFree(c->d_item_order);
+        c->d_item_order = nullptr;
+        c->item_order_capacity = 0;
+        CUDA_TRY(c, cudaMalloc(&c->d_item_order, traced.size() * sizeof(int)));
+        c->item_order_capacity = traced.size();
+    }
+    // a launch that still reads the previous table may be in flight on the stream: order the copy behind it
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    CUDA_TRY(c, cudaMemcpy(c->d_item_order, traced.data(), traced.size() * sizeof(int), cudaMemcpyHostToDevice));
+    c->item_order_key = key;
+    return B200PT_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -249,6 +332,7 @@ int b200pt_destroy(b200pt_context* c)
     free_target(c);
     free_env(c);
     if (c->d_work_counter) cudaFree(c->d_work_counter);
+    if (c->d_item_order) cudaFree(c->d_item_order);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < kRingSlots; i++) {
@@ -464,6 +548,12 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
         rp.num_cull_rects = compute_cull_rects_v4(c->scene_quads.data(), c->scenes.v4.numQuads, c->scene_spheres.data(),
                                                   c->scenes.v4.numSpheres, c->scene_cam, c->scene_cam[3], c->width, c->height, rp.cull_rect);
     else rp.num_cull_rects = compute_cull_rects(c->params.profile, c->width, c->height, rp.cull_rect);
+
+    {
+        const int rc = ensure_item_order(c, rp);
+        if (rc != B200PT_OK) return rc;
+        rp.item_order = c->item_order_key ? c->d_item_order : nullptr;
+    }
 
     LaunchConfig lc = launch_config(c);
     // persistent grid: every SM holds blocks_per_sm resident CTAs; warps pull 32-pixel items

@@ -153,6 +153,7 @@ struct RenderParams {
     uint32_t* screen;     // optional: row-major u32 image, tone-mapped in the kernel tail (OUTPUT_TO_SCREEN)
     int screen_mode;      // 0 = file packing, 1 = screen packing
     int* work_counter;    // atomic work-item counter: replaces work_queue.cpp's ring + CAS pop
+    const int* item_order; // optional: the k-th pulled work item is item_order[k] (expensive items first: see b200pt_capi.cu)
     DeviceCounters* counters;
     cudaTextureObject_t env;  // RGBA32F linear texture, texel t = reference float index 3t
     int env_w, env_h;

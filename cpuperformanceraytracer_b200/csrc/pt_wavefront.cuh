@@ -134,6 +134,7 @@ pt_render_sorted_kernel(const __grid_constant__ RenderParams p, const __grid_con
             if (item >= p.num_items) {
                 more_items = false;
             } else {
+                if (p.item_order) item = __ldg(p.item_order + item);
                 int gl = item * 4 + (lane >> 3);
                 if (p.block_items) {  // an 8x4 pixel block: see pt_render_kernel
                     const int per_tile = p.groups_per_tile >> 2;

@@ -106,7 +106,9 @@ typedef struct b200pt_params {
     int32_t generic_scene_tables;   /* 1: read the Cornell vertices from the scene table instead of the
                                        compile-time specialisation (A/B measurements; results are identical) */
     int32_t scheduler;              /* B200PT_SCHED_*: how paths are mapped to threads (results are identical) */
-    int32_t reserved[4];
+    int32_t disable_item_order;     /* 1: pull the work items in buffer order instead of scene-first / sky-last
+                                       (A/B measurements; results are identical) */
+    int32_t reserved[3];
 } b200pt_params;
 
 typedef struct b200pt_counters {

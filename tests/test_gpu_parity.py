@@ -256,6 +256,30 @@ def test_camera_culling_changes_nothing(oracle, profile, envshape, ek, es):
     assert res[0][2:] == res[1][2:]
 
 
+@pytest.mark.parametrize("sched", [api.SCHED_LANE, api.SCHED_SORTED], ids=["lane", "sorted"])
+def test_item_pull_order_changes_nothing(oracle, sched):
+    """scene-first / sky-last pull order of the work items (built once a geometry is launched twice in a row): the same
+    bits as buffer order -- image, RNG states, counters -- for whole images, tile ranges and strip-shaped items"""
+    for (W, H, ntx, nty) in ((640, 360, 4, 5), (648, 363, 3, 3)):  # tile height 72 (8x4 block items) / 121 (32x1 strips)
+        res = []
+        for off in (False, True):
+            with api.Renderer(profile=api.PROFILE_V2, num_bounces=8, disable_item_order=off, scheduler=sched) as r:
+                r.resize(W, H, ntx, nty)
+                for n in (2, 3, 4):          # the table is in use from the second launch of a geometry on
+                    r.render_frames(n)
+                r.set_tile_row_range(1, nty - 1)
+                for n in (1, 2, 2):
+                    r.render_frames(n)
+                c = r.counters()
+                res.append((r.download_target(), r.rng_state(), (c["paths"], c["segments"], c["escapes"], c["culled_segments"])))
+        assert np.array_equal(res[0][0], res[1][0]) and np.array_equal(res[0][1], res[1][1]) and res[0][2] == res[1][2]
+    o, _ = oracle.render(oracle.PROFILE_V2, 640, 360, 4, 5, 8, 6)
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=8, scheduler=sched) as r:
+        r.resize(640, 360, 4, 5)
+        r.render_frames(1); r.render_frames(2); r.render_frames(3)
+        assert np.array_equal(r.download_target(), o)
+
+
 def test_tile_row_bands_assemble_to_the_full_render(oracle):
     """tile-shard building block: rendering tile rows band by band == the full render, bit for bit."""
     W, H, ntx, nty, frames = 192, 120, 3, 5, 9
