@@ -109,8 +109,8 @@ int collect_timing(b200pt_context* c, bool wait)
 // The pull order of a launch's work items (RenderParams::item_order).  Items are pulled from one atomic counter; an
 // item that looks into the scene costs ~15x a sky-only one (camera-culled pixels never trace), so pulling the
 // expensive ones first leaves the cheap ones to even out the end of the launch -- what the reference gets from its
-// fine-grained per-tile queue (work_queue.cpp:7-66).  Classification: the item's pixel block against the culling
-// rectangles (conservative; the kernel still decides per pixel).  Returns 0 on success.
+// fine-grained per-tile queue (work_queue.cpp:7-66).  The table is built on the device (build_item_order_kernel,
+// pt_post.cu: a few microseconds, stream-ordered, no host synchronisation) whenever the launch geometry changes.
 int ensure_item_order(b200pt_context* c, const RenderParams& rp)
 {
     if (rp.num_cull_rects <= 0 || c->params.disable_item_order || rp.num_items < 2 * c->sm_count * 8) {
@@ -128,63 +128,21 @@ int ensure_item_order(b200pt_context* c, const RenderParams& rp)
     }
     if (key == 0) key = 1;
     if (key == c->item_order_key && c->d_item_order) return B200PT_OK;
-    // Build the table only for a geometry that is launched twice in a row: callers that walk over tile ranges (bands
-    // of a pipelined present, per-tile scheduling) change it on every launch and must not pay a rebuild + sync each time.
-    if (key != c->item_order_candidate) {
-        c->item_order_candidate = key;
+    if (rp.nframes < 8) {  // a new geometry for a few frames only (bands of a pipelined present): not worth two extra launches
         c->item_order_key = 0;
         return B200PT_OK;
     }
-    std::vector<int> traced, sky;
-    traced.reserve((size_t)rp.num_items);
-    const int per_tile = rp.groups_per_tile >> 2;
-    for (int item = 0; item < rp.num_items; item++) {
-        // pixel bounds of the item: an 8x4 block, or 4 consecutive groups of a tile row (pt_render_kernel's mapping)
-        int x0, x1, y0, y1;
-        if (rp.block_items) {
-            const int t = item / per_tile, it = item - t * per_tile;
-            const int band = it / rp.groups_per_tile_row, gx = it - band * rp.groups_per_tile_row;
-            const int g = rp.group_offset + t * rp.groups_per_tile + band * 4 * rp.groups_per_tile_row + gx;
-            const int tile = g / rp.groups_per_tile, r = g - tile * rp.groups_per_tile;
-            const int ty = tile / rp.num_tiles_x, tx = tile - ty * rp.num_tiles_x;
-            const int ly = r / rp.groups_per_tile_row, gxx = r - ly * rp.groups_per_tile_row;
-            x0 = tx * rp.tile_w + gxx * 8; x1 = x0 + 7;
-            y0 = ty * rp.tile_h + ly; y1 = y0 + 3;
-        } else {
-            const int g0 = rp.group_offset + item * 4;
-            int gl1 = item * 4 + 3;
-            if (gl1 >= rp.num_groups) gl1 = rp.num_groups - 1;
-            const int g1 = rp.group_offset + gl1;
-            auto pix = [&](int g, int& x, int& y) {
-                const int tile = g / rp.groups_per_tile, r = g - tile * rp.groups_per_tile;
-                const int ty = tile / rp.num_tiles_x, tx = tile - ty * rp.num_tiles_x;
-                const int ly = r / rp.groups_per_tile_row, gxx = r - ly * rp.groups_per_tile_row;
-                x = tx * rp.tile_w + gxx * 8; y = ty * rp.tile_h + ly;
-            };
-            int xa, ya, xb, yb;
-            pix(g0, xa, ya); pix(g1, xb, yb);
-            if (ya == yb) { x0 = xa; x1 = xb + 7; y0 = y1 = ya; }
-            else { x0 = 0; x1 = rp.width - 1; y0 = ya < yb ? ya : yb; y1 = ya < yb ? yb : ya; }  // wraps a row / a tile: be conservative
-        }
-        const float fx0 = (float)x0 - 0.5f, fx1 = (float)x1 + 0.5f;
-        const float fy0 = (float)(rp.height - 1 - y1) - 0.5f, fy1 = (float)(rp.height - 1 - y0) + 0.5f;  // flipped rows
-        bool hit = false;
-        for (int k = 0; k < rp.num_cull_rects && !hit; k++)
-            hit = fx1 >= rp.cull_rect[k].x && fx0 <= rp.cull_rect[k].z && fy1 >= rp.cull_rect[k].y && fy0 <= rp.cull_rect[k].w;
-        (hit ? traced : sky).push_back(item);
-    }
-    c->item_order_traced = (int)traced.size();
-    traced.insert(traced.end(), sky.begin(), sky.end());
-    if (c->item_order_capacity < traced.size()) {
-        if (c->d_item_order) cudaFree(c->d_item_order);
+    const size_t need = (size_t)rp.num_items + ((size_t)rp.num_items + 1023) / 1024;  // the table + per-block scratch
+    if (c->item_order_capacity < need) {
+        // launches that read the old table are ordered before the free on this stream
+        if (c->d_item_order) CUDA_TRY(c, cudaFreeAsync(c->d_item_order, c->stream));
         c->d_item_order = nullptr;
         c->item_order_capacity = 0;
-        CUDA_TRY(c, cudaMalloc(&c->d_item_order, traced.size() * sizeof(int)));
-        c->item_order_capacity = traced.size();
+        CUDA_TRY(c, cudaMallocAsync(&c->d_item_order, need * sizeof(int), c->stream));
+        c->item_order_capacity = need;
     }
-    // a launch that still reads the previous table may be in flight on the stream: order the copy behind it
-    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
-    CUDA_TRY(c, cudaMemcpy(c->d_item_order, traced.data(), traced.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUDA_TRY(c, launch_build_item_order(rp, c->d_item_order, c->stream));
+    c->launches += 2;
     c->item_order_key = key;
     return B200PT_OK;
 }
@@ -332,7 +290,7 @@ int b200pt_destroy(b200pt_context* c)
     free_target(c);
     free_env(c);
     if (c->d_work_counter) cudaFree(c->d_work_counter);
-    if (c->d_item_order) cudaFree(c->d_item_order);
+    if (c->d_item_order) cudaFreeAsync(c->d_item_order, c->own_stream);
     if (c->d_counters) cudaFree(c->d_counters);
     if (c->copy_stream) { cudaStreamSynchronize(c->copy_stream); cudaStreamDestroy(c->copy_stream); }
     for (int i = 0; i < kRingSlots; i++) {

@@ -50,8 +50,6 @@ struct b200pt_context {
     int* d_item_order = nullptr;
     size_t item_order_capacity = 0;
     unsigned long long item_order_key = 0;        // geometry the table on the device was built for (0 = none in use)
-    unsigned long long item_order_candidate = 0;  // geometry of the previous launch
-    int item_order_traced = 0;
     DeviceCounters* d_counters = nullptr;
     float* h_pinned = nullptr;  // staging for render_host (pinned, W*H*3 floats)
     uint32_t* h_pinned_screen = nullptr;

@@ -210,6 +210,7 @@ cudaError_t occupancy_sorted_fast(const LaunchConfig& lc, int* blocks_per_sm);
 cudaError_t launch_resolve_ldr(const float* target, uint32_t* out, int width, int height, int tile_w, int tile_h,
                                int num_tiles_x, int mode, cudaStream_t stream);
 cudaError_t launch_scale(float* target, size_t n, float scale, cudaStream_t stream);
+cudaError_t launch_build_item_order(const RenderParams& rp, int* order, cudaStream_t stream);
 cudaError_t launch_eval_portable(int op, const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
 cudaError_t launch_check_portable_tiers(int op, unsigned long long first, unsigned long long count, unsigned long long* counts,
                                         cudaStream_t stream);

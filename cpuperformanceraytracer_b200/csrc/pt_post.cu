@@ -4,6 +4,7 @@
 //                 fast variants (global_preprocessor_flags.h:62-63), exact rcp like the oracle.
 //   scale       : ACCUM_SUM epilogue after the cross-GPU sum (target *= 1/(N+1)).
 //   pack_env    : RGB f32 rows -> RGBA32F texels for the env texture object.
+//   build_item_order : the pull order of a launch's work items (scene-first, sky-last).
 // Compiled with --fmad=false so the tone map rounds like the reference's explicit fmadd sequence.
 #include "pt_common.cuh"
 #include "pt_tonemap.cuh"
@@ -41,6 +42,100 @@ __global__ void pack_env_kernel(const float* __restrict__ rgb, float4* __restric
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t k = i; k < texels; k += stride) rgba[k] = make_float4(rgb[3 * k], rgb[3 * k + 1], rgb[3 * k + 2], 0.f);
+}
+
+// Pull order of a launch's work items: the items whose pixel block touches a culling rectangle (they trace the
+// scene) first, in buffer order, then the sky-only ones, from the end of the table backwards.  Two small launches:
+// per-block counts, then every block sums the counts of the blocks before it and places its items (deterministic).
+__device__ __forceinline__ bool item_touches_scene(const RenderParams& rp, int item)
+{
+    // pixel bounds of the item: an 8x4 block, or 4 consecutive groups of a tile row (pt_render_kernel's mapping)
+    int x0, x1, y0, y1;
+    auto pix = [&](int g, int& x, int& y) {
+        const int tile = g / rp.groups_per_tile, r = g - tile * rp.groups_per_tile;
+        const int ty = tile / rp.num_tiles_x, tx = tile - ty * rp.num_tiles_x;
+        const int ly = r / rp.groups_per_tile_row, gx = r - ly * rp.groups_per_tile_row;
+        x = tx * rp.tile_w + gx * 8;
+        y = ty * rp.tile_h + ly;
+    };
+    if (rp.block_items) {
+        const int per_tile = rp.groups_per_tile >> 2;
+        const int t = item / per_tile, it = item - t * per_tile;
+        const int band = it / rp.groups_per_tile_row, gx = it - band * rp.groups_per_tile_row;
+        pix(rp.group_offset + t * rp.groups_per_tile + band * 4 * rp.groups_per_tile_row + gx, x0, y0);
+        x1 = x0 + 7;
+        y1 = y0 + 3;
+    } else {
+        int gl1 = item * 4 + 3;
+        if (gl1 >= rp.num_groups) gl1 = rp.num_groups - 1;
+        int xa, ya, xb, yb;
+        pix(rp.group_offset + item * 4, xa, ya);
+        pix(rp.group_offset + gl1, xb, yb);
+        if (ya == yb) { x0 = xa; x1 = xb + 7; y0 = y1 = ya; }
+        else { x0 = 0; x1 = rp.width - 1; y0 = min(ya, yb); y1 = max(ya, yb); }  // wraps a row / a tile: be conservative
+    }
+    const float fx0 = (float)x0 - 0.5f, fx1 = (float)x1 + 0.5f;
+    const float fy0 = (float)(rp.height - 1 - y1) - 0.5f, fy1 = (float)(rp.height - 1 - y0) + 0.5f;  // flipped rows
+    bool hit = false;
+    for (int k = 0; k < rp.num_cull_rects; k++)
+        hit = hit || (fx1 >= rp.cull_rect[k].x && fx0 <= rp.cull_rect[k].z && fy1 >= rp.cull_rect[k].y && fy0 <= rp.cull_rect[k].w);
+    return hit;
+}
+
+constexpr int kOrderBlock = 1024;
+
+__global__ void __launch_bounds__(kOrderBlock) count_scene_items_kernel(const __grid_constant__ RenderParams rp, int* __restrict__ block_counts)
+{
+    const int item = blockIdx.x * kOrderBlock + threadIdx.x;
+    const bool hit = item < rp.num_items && item_touches_scene(rp, item);
+    const int n = __syncthreads_count(hit);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = n;
+}
+
+__global__ void __launch_bounds__(kOrderBlock) place_items_kernel(const __grid_constant__ RenderParams rp, const int* __restrict__ block_counts,
+                                                                  int* __restrict__ order)
+{
+    __shared__ int warp_count[kOrderBlock / 32];
+    __shared__ int before_block;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // scene items of the blocks before this one
+    int part = 0;
+    for (int b = tid; b < (int)blockIdx.x; b += kOrderBlock) part += block_counts[b];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    if (lane == 0) warp_count[warp] = part;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < kOrderBlock / 32; w++) t += warp_count[w];
+        before_block = t;
+    }
+    __syncthreads();
+    const int scene_before = before_block, first = blockIdx.x * kOrderBlock;
+    const int sky_before = first - scene_before;
+    const int item = first + tid;
+    const bool valid = item < rp.num_items, hit = valid && item_touches_scene(rp, item);
+    const unsigned bt = __ballot_sync(0xffffffffu, hit), bs = __ballot_sync(0xffffffffu, valid && !hit);
+    __syncthreads();
+    if (lane == 0) warp_count[warp] = __popc(bt) | (__popc(bs) << 16);
+    __syncthreads();
+    int before_t = 0, before_s = 0;
+    for (int w = 0; w < warp; w++) {
+        before_t += warp_count[w] & 0xffff;
+        before_s += warp_count[w] >> 16;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+    if (hit) order[scene_before + before_t + __popc(bt & lt)] = item;
+    else if (valid) order[rp.num_items - 1 - (sky_before + before_s + __popc(bs & lt))] = item;
+}
+
+// `order` holds num_items ints followed by ceil(num_items / 1024) ints of scratch
+cudaError_t launch_build_item_order(const RenderParams& rp, int* order, cudaStream_t stream)
+{
+    const int blocks = (rp.num_items + kOrderBlock - 1) / kOrderBlock;
+    int* counts = order + rp.num_items;
+    count_scene_items_kernel<<<blocks, kOrderBlock, 0, stream>>>(rp, counts);
+    place_items_kernel<<<blocks, kOrderBlock, 0, stream>>>(rp, counts, order);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_resolve_ldr(const float* target, uint32_t* out, int width, int height, int tile_w, int tile_h,

@@ -258,17 +258,17 @@ def test_camera_culling_changes_nothing(oracle, profile, envshape, ek, es):
 
 @pytest.mark.parametrize("sched", [api.SCHED_LANE, api.SCHED_SORTED], ids=["lane", "sorted"])
 def test_item_pull_order_changes_nothing(oracle, sched):
-    """scene-first / sky-last pull order of the work items (built once a geometry is launched twice in a row): the same
+    """scene-first / sky-last pull order of the work items (a table built on the device per launch geometry): the same
     bits as buffer order -- image, RNG states, counters -- for whole images, tile ranges and strip-shaped items"""
     for (W, H, ntx, nty) in ((640, 360, 4, 5), (648, 363, 3, 3)):  # tile height 72 (8x4 block items) / 121 (32x1 strips)
         res = []
         for off in (False, True):
             with api.Renderer(profile=api.PROFILE_V2, num_bounces=8, disable_item_order=off, scheduler=sched) as r:
                 r.resize(W, H, ntx, nty)
-                for n in (2, 3, 4):          # the table is in use from the second launch of a geometry on
+                for n in (2, 9, 4):          # built by the first launch of >= 8 frames on a geometry, reused afterwards
                     r.render_frames(n)
                 r.set_tile_row_range(1, nty - 1)
-                for n in (1, 2, 2):
+                for n in (8, 2, 2):
                     r.render_frames(n)
                 c = r.counters()
                 res.append((r.download_target(), r.rng_state(), (c["paths"], c["segments"], c["escapes"], c["culled_segments"])))
@@ -278,6 +278,10 @@ def test_item_pull_order_changes_nothing(oracle, sched):
         r.resize(640, 360, 4, 5)
         r.render_frames(1); r.render_frames(2); r.render_frames(3)
         assert np.array_equal(r.download_target(), o)
+        o12, _ = oracle.render(oracle.PROFILE_V2, 640, 360, 4, 5, 8, 12)
+        r.reset()
+        r.render_frames(12)   # one launch, ordered pull
+        assert np.array_equal(r.download_target(), o12)
 
 
 def test_tile_row_bands_assemble_to_the_full_render(oracle):
