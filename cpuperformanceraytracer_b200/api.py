@@ -13,7 +13,7 @@ import numpy as np
 PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(PKG, "libb200pt.so")
 
-PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_OPT_V4, PROFILE_V3_REDO = 0, 1, 2, 3
+PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_OPT_V4, PROFILE_V3_REDO, PROFILE_V3_REDO_SCENE0 = 0, 1, 2, 3, 4
 MATH_PARITY, MATH_FAST = 0, 1
 ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
 SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_present_blocking", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
+    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_set_tile_stride", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_present_blocking", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
     "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_scale_target", "b200pt_scale_target_span",
     "b200pt_group_create", "b200pt_group_destroy", "b200pt_group_size", "b200pt_group_context", "b200pt_group_set_env",
     "b200pt_group_resize", "b200pt_group_reset", "b200pt_group_set_bands", "b200pt_group_set_frame_counter", "b200pt_group_get_frame_counter",
@@ -101,6 +101,7 @@ def load_library():
     L.b200pt_finalize_sum.argtypes = [vp, i32]
     L.b200pt_set_tile_row_range.argtypes = [vp, i32, i32]
     L.b200pt_set_tile_range.argtypes = [vp, i32, i32]
+    L.b200pt_set_tile_stride.argtypes = [vp, i32, i32]
     L.b200pt_set_scene_v4.argtypes = [vp, vp, i32, vp, i32, vp, vp]
     L.b200pt_present_submit.argtypes = [vp, i32]
     L.b200pt_present_acquire.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(i32)]
@@ -355,6 +356,9 @@ class Renderer:
 
     def set_tile_range(self, first_flat_tile, num_tiles):
         self._check(self._lib.b200pt_set_tile_range(self._ctx, int(first_flat_tile), int(num_tiles)), "b200pt_set_tile_range")
+
+    def set_tile_stride(self, remainder, modulus):
+        self._check(self._lib.b200pt_set_tile_stride(self._ctx, int(remainder), int(modulus)), "b200pt_set_tile_stride")
 
     def finalize_sum(self, total_frames):
         self._check(self._lib.b200pt_finalize_sum(self._ctx, int(total_frames)), "b200pt_finalize_sum")

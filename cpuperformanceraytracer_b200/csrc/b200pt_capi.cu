@@ -13,7 +13,7 @@ namespace {
 
 bool uses_env(const b200pt_params& p)
 {
-    if (p.profile == B200PT_PROFILE_SIMT_TEXTURED || p.profile == B200PT_PROFILE_V3_REDO) return true;
+    if (p.profile == B200PT_PROFILE_SIMT_TEXTURED || p.profile == B200PT_PROFILE_V3_REDO || p.profile == B200PT_PROFILE_V3_REDO_SCENE0) return true;
     return p.profile == B200PT_PROFILE_OPT_V4 && p.env_kind != B200PT_ENV_NONE;
 }
 
@@ -29,16 +29,17 @@ LaunchConfig launch_config(const b200pt_context* c)
 {
     LaunchConfig lc{};
     lc.profile = c->params.profile;
-    lc.env_kind = (c->params.profile == B200PT_PROFILE_SIMT_TEXTURED || c->params.profile == B200PT_PROFILE_V3_REDO) ? kEnvEquirect
+    lc.env_kind = (c->params.profile == B200PT_PROFILE_SIMT_TEXTURED || is_v3redo(c->params.profile)) ? kEnvEquirect
                  : c->params.profile == B200PT_PROFILE_V2           ? kEnvNone
                                                                     : c->params.env_kind;
-    lc.env_sampler = c->params.profile == B200PT_PROFILE_V3_REDO ? kSamplerBilinear
+    lc.env_sampler = is_v3redo(c->params.profile) ? kSamplerBilinear
                      : (c->params.profile == B200PT_PROFILE_OPT_V4 && c->params.env_kind != B200PT_ENV_NONE) ? c->params.env_sampler
                                                                                                               : kSamplerPoint;
     lc.accum_mode = c->params.accum_mode;
     lc.static_scene = (c->params.generic_scene_tables || c->custom_scene) ? 0 : 1;
     if (lc.profile == kProfileV4 && lc.static_scene && !v4_scene_matches_static_tables(c->scenes.v4)) lc.static_scene = 0;
     if (lc.static_scene && lc.profile == kProfileV3Redo && !v3redo_spheres_match_static_tables(c->scenes.v3redo.sphere)) lc.static_scene = 0;
+    if (lc.static_scene && lc.profile == kProfileV3RedoS0 && !v3redo0_spheres_match_static_tables(c->scenes.v3redo0.sphere)) lc.static_scene = 0;
     if (lc.static_scene && (lc.profile == kProfileV2 || lc.profile == kProfileSimtTextured) &&
         !cornell_spheres_match_static_tables(c->scenes.cornell.sphere))
         lc.static_scene = 0;
@@ -113,14 +114,16 @@ int collect_timing(b200pt_context* c, bool wait)
 // pt_post.cu: a few microseconds, stream-ordered, no host synchronisation) whenever the launch geometry changes.
 int ensure_item_order(b200pt_context* c, const RenderParams& rp)
 {
-    if (rp.num_cull_rects <= 0 || c->params.disable_item_order || rp.num_items < 2 * c->sm_count * 8) {
+    const bool strided = rp.tile_mod > 1;  // the table then also says WHICH items the launch renders: mandatory
+    if (!strided && (rp.num_cull_rects <= 0 || c->params.disable_item_order || rp.num_items < 2 * c->sm_count * 8)) {
         c->item_order_key = 0;
         return B200PT_OK;  // nothing to gain: launch without an order table
     }
     unsigned long long key = 1469598103934665603ull;
     auto mix = [&](unsigned long long v) { key = (key ^ v) * 1099511628211ull; };
     mix((unsigned)rp.width); mix((unsigned)rp.height); mix((unsigned)rp.tile_w); mix((unsigned)rp.tile_h); mix((unsigned)rp.num_tiles_x);
-    mix((unsigned)rp.group_offset); mix((unsigned)rp.num_groups); mix((unsigned)rp.block_items); mix((unsigned)rp.num_cull_rects);
+    mix((unsigned)rp.group_offset); mix((unsigned)rp.num_groups); mix((unsigned)rp.block_items); mix((unsigned)(rp.num_cull_rects + 1));
+    mix((unsigned)rp.tile_mod); mix((unsigned)rp.tile_rem); mix((unsigned)rp.num_items);
     for (int k = 0; k < rp.num_cull_rects; k++) {
         unsigned u[4];
         std::memcpy(u, &rp.cull_rect[k], sizeof(u));
@@ -128,11 +131,11 @@ int ensure_item_order(b200pt_context* c, const RenderParams& rp)
     }
     if (key == 0) key = 1;
     if (key == c->item_order_key && c->d_item_order) return B200PT_OK;
-    if (rp.nframes < 8) {  // a new geometry for a few frames only (bands of a pipelined present): not worth two extra launches
+    if (rp.nframes < 8 && !strided) {  // a new geometry for a few frames only (bands of a pipelined present): not worth two extra launches
         c->item_order_key = 0;
         return B200PT_OK;
     }
-    const size_t need = (size_t)rp.num_items + ((size_t)rp.num_items + 1023) / 1024;  // the table + per-block scratch
+    const size_t need = (size_t)rp.num_items + ((size_t)rp.order_domain_items + 1023) / 1024;  // the table + per-block scratch
     if (c->item_order_capacity < need) {
         // launches that read the old table are ordered before the free on this stream
         if (c->d_item_order) CUDA_TRY(c, cudaFreeAsync(c->d_item_order, c->stream));
@@ -169,7 +172,7 @@ const char* b200pt_last_error(b200pt_context* ctx) { return ctx ? ctx->last_erro
 
 int b200pt_default_params(int profile, b200pt_params* p)
 {
-    if (!p || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_V3_REDO) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!p || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_V3_REDO_SCENE0) return B200PT_ERR_INVALID_ARGUMENT;
     std::memset(p, 0, sizeof(*p));
     p->struct_size = (int32_t)sizeof(b200pt_params);
     p->device = 0;
@@ -184,7 +187,7 @@ int b200pt_default_params(int profile, b200pt_params* p)
     } else if (profile == B200PT_PROFILE_SIMT_TEXTURED) {
         p->env_kind = B200PT_ENV_EQUIRECT;
         p->env_sampler = B200PT_SAMPLER_POINT;
-    } else if (profile == B200PT_PROFILE_V3_REDO) {
+    } else if (profile == B200PT_PROFILE_V3_REDO || profile == B200PT_PROFILE_V3_REDO_SCENE0) {
         p->env_kind = B200PT_ENV_EQUIRECT;  // EquirectangularTextureSampleBilinear, v3_redo.cpp:638
         p->env_sampler = B200PT_SAMPLER_BILINEAR;
     }
@@ -196,7 +199,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     if (!params || !out_ctx) return B200PT_ERR_INVALID_ARGUMENT;
     *out_ctx = nullptr;
     if (params->struct_size != (int32_t)sizeof(b200pt_params)) return B200PT_ERR_INVALID_ARGUMENT;
-    if (params->profile < B200PT_PROFILE_V2 || params->profile > B200PT_PROFILE_V3_REDO) return B200PT_ERR_INVALID_ARGUMENT;
+    if (params->profile < B200PT_PROFILE_V2 || params->profile > B200PT_PROFILE_V3_REDO_SCENE0) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->math_mode != B200PT_MATH_PARITY && params->math_mode != B200PT_MATH_FAST) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->accum_mode != B200PT_ACCUM_RUNNING_AVERAGE && params->accum_mode != B200PT_ACCUM_SUM) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->profile == B200PT_PROFILE_OPT_V4) {
@@ -208,7 +211,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     b200pt_context* c = new (std::nothrow) b200pt_context();
     if (!c) return B200PT_ERR_OUT_OF_MEMORY;
     c->params = *params;
-    if (c->params.num_bounces < 0) c->params.num_bounces = (params->profile == B200PT_PROFILE_OPT_V4 || params->profile == B200PT_PROFILE_V3_REDO) ? 8 : 4;
+    if (c->params.num_bounces < 0) c->params.num_bounces = (params->profile == B200PT_PROFILE_OPT_V4 || is_v3redo(params->profile)) ? 8 : 4;
     c->device = params->device;
 
     int ndev = 0;
@@ -248,6 +251,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     build_cornell_scene(&c->scenes.cornell, params->profile == B200PT_PROFILE_SIMT_TEXTURED);
     build_v4_scene(&c->scenes.v4);
     build_v3redo_scene(&c->scenes.v3redo);
+    build_v3redo_scene0(&c->scenes.v3redo0);
 
     LaunchConfig lc = launch_config(c);
     int bps = 0;
@@ -414,6 +418,7 @@ int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx,
     c->tile_w = width / ntx;
     c->tile_h = height / nty;
     c->first_tile = c->num_tiles = 0;
+    c->tile_mod = c->tile_rem = 0;
     // frames still in the present ring belong to the old image
     CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));
     c->submitted = c->acquired = 0;
@@ -489,6 +494,23 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     rp.num_groups = ntiles * rp.groups_per_tile;
     rp.num_items = (rp.num_groups + 3) / 4;
     rp.block_items = (c->tile_h % 4 == 0) ? 1 : 0;
+    rp.order_domain_items = rp.num_items;
+    long long launch_groups = rp.num_groups;
+    if (c->tile_mod > 1) {
+        // every tile_mod-th tile of the whole image: the kernel walks the image's item space through the order table
+        if (rp.groups_per_tile % 4) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "a tile stride needs tiles of a multiple of 32 pixels");
+        const int all_tiles = c->ntx * c->nty;
+        const int mine = c->tile_rem < all_tiles ? (all_tiles - c->tile_rem + c->tile_mod - 1) / c->tile_mod : 0;
+        rp.tile_mod = c->tile_mod;
+        rp.tile_rem = c->tile_rem;
+        rp.order_domain_items = rp.num_items;
+        rp.num_items = mine * (rp.groups_per_tile / 4);
+        launch_groups = (long long)mine * rp.groups_per_tile;
+        if (mine == 0) {  // nothing to render on this context: the frame counter still advances
+            c->iframe += nframes;
+            return B200PT_OK;
+        }
+    }
     rp.first_frame = c->iframe + 1;  // iFrame += 1 before the render, v4.cpp:1703
     rp.nframes = nframes;
     rp.num_bounces = c->params.num_bounces;
@@ -539,7 +561,7 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     c->timing_pending[ts] = true;
     c->launches++;
     c->iframe += nframes;
-    c->paths += (uint64_t)rp.num_groups * 8u * (uint64_t)nframes;
+    c->paths += (uint64_t)launch_groups * 8u * (uint64_t)nframes;
 
     return B200PT_OK;
 }
@@ -707,7 +729,7 @@ int b200pt_present_blocking(b200pt_context* c, int32_t nframes, uint32_t* host_f
 {
     if (!c || nframes <= 0 || !host_frame || bands < -1) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    if (c->num_tiles > 0) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "a tile range is set: the blocking present renders the whole image");
+    if (c->num_tiles > 0 || c->tile_mod > 1) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "a tile range is set: the blocking present renders the whole image");
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     if (bands == -1) {
@@ -792,6 +814,7 @@ int b200pt_set_tile_row_range(b200pt_context* c, int32_t first_tile_row, int32_t
         return fail(c, B200PT_ERR_INVALID_ARGUMENT, "tile row range outside the image");
     c->first_tile = first_tile_row * c->ntx;
     c->num_tiles = num_tile_rows * c->ntx;
+    c->tile_mod = c->tile_rem = 0;
     return B200PT_OK;
 }
 
@@ -803,6 +826,21 @@ int b200pt_set_tile_range(b200pt_context* c, int32_t first_flat_tile, int32_t nu
         return fail(c, B200PT_ERR_INVALID_ARGUMENT, "tile range outside the image");
     c->first_tile = first_flat_tile;
     c->num_tiles = num_tiles;
+    c->tile_mod = c->tile_rem = 0;
+    return B200PT_OK;
+}
+
+int b200pt_set_tile_stride(b200pt_context* c, int32_t remainder, int32_t modulus)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    if (modulus < 0 || remainder < 0 || (modulus > 0 && remainder >= modulus))
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "need 0 <= remainder < modulus (0, 0 = all tiles)");
+    if (modulus > 1 && ((c->tile_w / 8) * c->tile_h) % 4)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "a tile stride needs tiles of a multiple of 32 pixels");
+    c->tile_mod = modulus > 1 ? modulus : 0;
+    c->tile_rem = modulus > 1 ? remainder : 0;
+    c->first_tile = c->num_tiles = 0;
     return B200PT_OK;
 }
 
@@ -915,13 +953,18 @@ int b200pt_static_tables_match(int profile)
         build_v3redo_scene(&s);
         return v3redo_spheres_match_static_tables(s.sphere) ? 1 : 0;
     }
+    case B200PT_PROFILE_V3_REDO_SCENE0: {
+        V3RedoScene0 s;
+        build_v3redo_scene0(&s);
+        return v3redo0_spheres_match_static_tables(s.sphere) ? 1 : 0;
+    }
     default: return -1;
     }
 }
 
 int b200pt_compute_cull_rects(int profile, int32_t width, int32_t height, float* rects, int32_t* count)
 {
-    if (!rects || !count || width <= 0 || height <= 0 || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_V3_REDO)
+    if (!rects || !count || width <= 0 || height <= 0 || profile < B200PT_PROFILE_V2 || profile > B200PT_PROFILE_V3_REDO_SCENE0)
         return B200PT_ERR_INVALID_ARGUMENT;
     float4 r[kMaxCullRects];
     const int n = compute_cull_rects(profile, width, height, r);

@@ -145,7 +145,9 @@ struct b200pt_group {
     bool combine_timing_pending = false;
     double combine_ms = 0.0;
     int width = 0, height = 0, ntx = 0, nty = 0;
-    int tile_first[kMaxGroup] = {}, tile_count[kMaxGroup] = {};  // B200PT_SHARD_TILES: flat tile ranges
+    int tile_first[kMaxGroup] = {}, tile_count[kMaxGroup] = {};  // B200PT_SHARD_TILES: flat tile ranges ...
+    bool tile_stride = false;  // ... or rank r renders the tiles with FlatTileIndex % n == r (interleaved: balanced by construction)
+    bool peer_all = true;      // every rank can address rank 0's memory
     int iframe = 0;
     uint64_t launches = 0;  // combine kernels (the contexts count their own)
     float* h_pinned = nullptr;  // staging of b200pt_group_render_host for pageable caller buffers
@@ -373,14 +375,26 @@ int render_tiles(b200pt_group* g, int nframes, bool gather)
         GROUP_CUDA(g, cudaEventRecord(g->cb0, g->ctx[0]->stream));
     }
     if (gather) {
+        const size_t per_tile = (size_t)(g->width / g->ntx) * (size_t)(g->height / g->nty) * 3;
         for (int r = 1; r < n; r++) {
-            size_t off, cnt;
-            tile_span(g, r, &off, &cnt);
-            if (cnt == 0) continue;
+            if (g->tile_count[r] == 0) continue;
             DeviceGuard guard(g->device[r]);
             GROUP_CUDA(g, guard.status);
-            GROUP_CUDA(g, cudaMemcpyPeerAsync(g->ctx[0]->d_target + off, g->device[0], g->ctx[r]->d_target + off, g->device[r],
-                                              cnt * sizeof(float), g->ctx[r]->stream));
+            if (g->tile_stride && g->peer_all) {
+                // one kernel per rank: its interleaved tiles stored straight into rank 0's buffer over NVLink peer memory
+                GROUP_CUDA(g, launch_tile_gather(g->ctx[r]->d_target, g->ctx[0]->d_target, g->ntx * g->nty, n, r, per_tile, g->ctx[r]->sm_count,
+                                                 g->ctx[r]->stream));
+                g->launches++;
+            } else if (g->tile_stride) {
+                for (int t = r; t < g->ntx * g->nty; t += n)
+                    GROUP_CUDA(g, cudaMemcpyPeerAsync(g->ctx[0]->d_target + (size_t)t * per_tile, g->device[0], g->ctx[r]->d_target + (size_t)t * per_tile,
+                                                      g->device[r], per_tile * sizeof(float), g->ctx[r]->stream));
+            } else {
+                size_t off, cnt;
+                tile_span(g, r, &off, &cnt);
+                GROUP_CUDA(g, cudaMemcpyPeerAsync(g->ctx[0]->d_target + off, g->device[0], g->ctx[r]->d_target + off, g->device[r],
+                                                  cnt * sizeof(float), g->ctx[r]->stream));
+            }
             GROUP_CUDA(g, cudaEventRecord(g->combine_done[r], g->ctx[r]->stream));
             const int rc = stream_wait(g, 0, g->combine_done[r]);
             if (rc != B200PT_OK) return rc;
@@ -453,6 +467,7 @@ int b200pt_group_create(const b200pt_params* params, const int32_t* devices, int
                 if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
                 else if (e != cudaSuccess) can = 0;
             }
+            if (!can) g->peer_all = false;
             if (!can && sharding == B200PT_SHARD_SPP && combine == B200PT_COMBINE_PEER) rc = B200PT_ERR_CUDA;
         }
     }
@@ -534,8 +549,18 @@ int b200pt_group_resize(b200pt_group* g, int32_t width, int32_t height, int32_t 
     g->ntx = ntx;
     g->nty = nty;
     g->iframe = 0;
-    if (g->sharding == B200PT_SHARD_TILES) {
-        // Contiguous flat-tile ranges (one span of the buffer per rank) of near-equal COST, not near-equal size: a tile
+    g->tile_stride = false;
+    if (g->sharding == B200PT_SHARD_TILES && g->n > 1 && (((width / ntx) / 8) * (height / nty)) % 4 == 0) {
+        // Interleaved tiles: rank r renders the tiles with FlatTileIndex % n == r, in one launch (the pull-order table lists
+        // them).  Cheap sky tiles and expensive scene tiles spread evenly over the ranks without any cost model.
+        g->tile_stride = true;
+        for (int r = 0; r < g->n; r++) {
+            g->tile_first[r] = r;
+            g->tile_count[r] = r < ntx * nty ? (ntx * nty - r + g->n - 1) / g->n : 0;
+            GROUP_CTX(g, r, b200pt_set_tile_stride(g->ctx[r], r, g->n));
+        }
+    } else if (g->sharding == B200PT_SHARD_TILES) {
+        // Tiles of another shape (items would straddle tiles): contiguous flat-tile ranges (one span of the buffer per rank) of near-equal COST, not near-equal size: a tile
         // of sky pixels (camera-culled: no scene trace) is ~10x cheaper than a tile looking into the scene, and the
         // reference's images have the sky at the top and the scene in the middle.
         const int ntiles = ntx * nty;
@@ -702,8 +727,24 @@ int b200pt_group_render_host(b200pt_group* g, float* BufferOut, int32_t W, int32
         DeviceGuard guard(g->device[0]);
         GROUP_CUDA(g, guard.status);
         GROUP_CUDA(g, cudaMemcpyAsync(src, c0->d_target, nfl * sizeof(float), cudaMemcpyDeviceToHost, c0->stream));
+    } else if (g->tile_stride) {
+        // interleaved tiles: every rank takes the whole state over its own PCIe link (its tiles are spread all over the
+        // buffer), the finished tiles meet on rank 0 (tile_gather_kernel), one copy back
+        for (int r = 0; r < g->n; r++) {
+            if (g->tile_count[r] == 0) continue;
+            DeviceGuard guard(g->device[r]);
+            GROUP_CUDA(g, guard.status);
+            GROUP_CUDA(g, cudaMemcpyAsync(g->ctx[r]->d_target, src, nfl * sizeof(float), cudaMemcpyHostToDevice, g->ctx[r]->stream));
+        }
+        if (nframes > 0) {
+            const int rc = render_tiles(g, nframes, true);
+            if (rc != B200PT_OK) return rc;
+        }
+        DeviceGuard guard(g->device[0]);
+        GROUP_CUDA(g, guard.status);
+        GROUP_CUDA(g, cudaMemcpyAsync(src, g->ctx[0]->d_target, nfl * sizeof(float), cudaMemcpyDeviceToHost, g->ctx[0]->stream));
     } else {
-        // tile sharding needs no GPU-to-GPU traffic at all on this path: every rank moves its own span of the
+        // contiguous tile ranges need no GPU-to-GPU traffic at all on this path: every rank moves its own span of the
         // caller's buffer over its own PCIe link, in both directions
         for (int r = 0; r < g->n; r++) {
             size_t off, cnt;
@@ -733,7 +774,7 @@ int b200pt_group_render_host(b200pt_group* g, float* BufferOut, int32_t W, int32
     if (!direct) std::memcpy(BufferOut, g->h_pinned, nfl * sizeof(float));
     if (ScreenBufferData && g->ctx[0]->params.output_to_screen) {
         // OUTPUT_TO_SCREEN: the tone-mapped frame of the combined image (the per-rank kernels only saw partial sums)
-        if (g->sharding == B200PT_SHARD_TILES) {
+        if (g->sharding == B200PT_SHARD_TILES && !g->tile_stride) {
             // rank 0 needs the other ranks' spans for the tone map
             GROUP_CTX(g, 0, b200pt_upload_target(g->ctx[0], BufferOut));
         }

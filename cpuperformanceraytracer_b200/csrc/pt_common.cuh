@@ -138,6 +138,34 @@ constexpr float kV3QuadVerts[kV3Quads][4][3] = {
     {{-5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, -2.5f}, {-5.0f, 12.4f, -2.5f}}};
 constexpr float kV3Translation[kV3Quads][3] = {{0.0f, 0.0f, 10.0f}, {0.0f, 0.0f, 0.0f}, {0.0f, 0.0f, 10.0f}, {0.0f, 0.0f, 10.0f}};
 
+// The same renderer compiled with `#define SCENE 0` (v3_redo.cpp:379, :392-479, :530-580): the Cornell box of v2 (no
+// translation: the camera sits at (0, 0, 40) and looks down -z), a light far outside the box, three spheres with
+// Fresnel-specular materials.
+constexpr int kV3S0Quads = 6;
+constexpr int kV3S0Spheres = 3;
+constexpr int kV3S0Objects = kV3S0Quads + kV3S0Spheres;
+constexpr float kV3S0QuadVerts[kV3S0Quads][4][3] = {
+    {{-12.6f, -12.6f, 25.0f}, {12.6f, -12.6f, 25.0f}, {12.6f, 12.6f, 25.0f}, {-12.6f, 12.6f, 25.0f}},        // back wall
+    {{-12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 15.0f}, {-12.6f, -12.45f, 15.0f}},  // floor
+    {{-12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 15.0f}, {-12.6f, 12.5f, 15.0f}},          // ceiling
+    {{-12.5f, -12.6f, 25.0f}, {-12.5f, -12.6f, 15.0f}, {-12.5f, 12.6f, 15.0f}, {-12.5f, 12.6f, 25.0f}},      // left wall
+    {{12.5f, -12.6f, 25.0f}, {12.5f, -12.6f, 15.0f}, {12.5f, 12.6f, 15.0f}, {12.5f, 12.6f, 25.0f}},          // right wall
+    {{-5.0f, 12.4f, -22.5f}, {5.0f, 12.4f, -22.5f}, {5.0f, 12.4f, -17.5f}, {-5.0f, 12.4f, -17.5f}}};         // light
+constexpr float kV3S0SphereY = -9.5f, kV3S0SphereZ = 20.0f, kV3S0SphereRadius = 3.0f;  // x = cornell_sphere_x(i)
+struct V3RedoScene0 {
+    LegacyQuad quad[kV3S0Quads];
+    float4 sphere[kV3S0Spheres];
+    V4Material mat[kV3S0Objects];
+    v3 cameraPosition;
+};
+inline bool v3redo0_spheres_match_static_tables(const float4* sphere)
+{
+    for (int i = 0; i < kV3S0Spheres; i++)
+        if (sphere[i].x != cornell_sphere_x(i) || sphere[i].y != kV3S0SphereY || sphere[i].z != kV3S0SphereZ || sphere[i].w != kV3S0SphereRadius)
+            return false;
+    return true;
+}
+
 constexpr int kMaxCullRects = 12;
 
 struct DeviceCounters {
@@ -163,7 +191,9 @@ struct RenderParams {
     int groups_per_tile;      // tile_w / 8 * tile_h
     int num_groups;           // SoA8 groups rendered by this launch (whole image, or a band of tile rows)
     int group_offset;         // first group of the band (tile-shard: a rank's tile rows are contiguous)
-    int num_items;            // ceil(num_groups / 4): one warp = 4 groups = 32 pixels
+    int num_items;            // work items of this launch (ceil(num_groups / 4): one warp = 4 groups = 32 pixels; fewer with a tile stride)
+    int tile_mod, tile_rem;   // tile_mod > 1: only tiles with FlatTileIndex % tile_mod == tile_rem (the items come from item_order)
+    int order_domain_items;   // items the pull-order builder classifies: num_items, or all items of the image with a tile stride
     int block_items;          // tile_h % 4 == 0: an item is an 8x4 pixel block (4 groups stacked in y) instead of a 32x1 strip
     int first_frame;          // 1-based iFrame of the first render call in this launch
     int nframes;
@@ -179,7 +209,8 @@ struct RenderParams {
     float4 cull_rect[kMaxCullRects];
 };
 
-enum : int { kProfileV2 = 0, kProfileSimtTextured = 1, kProfileV4 = 2, kProfileV3Redo = 3 };
+enum : int { kProfileV2 = 0, kProfileSimtTextured = 1, kProfileV4 = 2, kProfileV3Redo = 3, kProfileV3RedoS0 = 4 };
+__host__ __device__ constexpr bool is_v3redo(int profile) { return profile == kProfileV3Redo || profile == kProfileV3RedoS0; }
 enum : int { kEnvNone = 0, kEnvEquirect = 1, kEnvCubemap = 2 };
 enum : int { kSamplerPoint = 0, kSamplerBilinear = 1, kSamplerRandom = 2 };
 enum : int { kAccumAverage = 0, kAccumSum = 1 };
@@ -195,6 +226,7 @@ struct SceneSet {
     CornellScene cornell;
     V4Scene v4;
     V3RedoScene v3redo;
+    V3RedoScene0 v3redo0;
 };
 cudaError_t launch_render_parity(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
 cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
@@ -211,6 +243,8 @@ cudaError_t launch_resolve_ldr(const float* target, uint32_t* out, int width, in
                                int num_tiles_x, int mode, cudaStream_t stream);
 cudaError_t launch_scale(float* target, size_t n, float scale, cudaStream_t stream);
 cudaError_t launch_build_item_order(const RenderParams& rp, int* order, cudaStream_t stream);
+cudaError_t launch_tile_gather(const float* src, float* dst, int num_tiles, int mod, int rem, size_t floats_per_tile, int sm_count,
+                               cudaStream_t stream);
 cudaError_t launch_eval_portable(int op, const float* a, const float* b, float* out, size_t n, cudaStream_t stream);
 cudaError_t launch_check_portable_tiers(int op, unsigned long long first, unsigned long long count, unsigned long long* counts,
                                         cudaStream_t stream);

@@ -12,6 +12,8 @@ cudaError_t launch_render_parity(const LaunchConfig& lc, const RenderParams& rp,
             kernel<<<lc.grid, lc.block, 0, stream>>>(rp, scenes.v4);
         } else if constexpr (std::is_same<KernelT, void (*)(RenderParams, V3RedoScene)>::value) {
             kernel<<<lc.grid, lc.block, 0, stream>>>(rp, scenes.v3redo);
+        } else if constexpr (std::is_same<KernelT, void (*)(RenderParams, V3RedoScene0)>::value) {
+            kernel<<<lc.grid, lc.block, 0, stream>>>(rp, scenes.v3redo0);
         } else {
             kernel<<<lc.grid, lc.block, 0, stream>>>(rp, scenes.cornell);
         }

@@ -84,57 +84,94 @@ __device__ __forceinline__ bool item_touches_scene(const RenderParams& rp, int i
 
 constexpr int kOrderBlock = 1024;
 
+// does the launch render this item at all (tile stride), and does it touch the scene
+__device__ __forceinline__ void classify_item(const RenderParams& rp, int item, bool& mine, bool& scene)
+{
+    mine = item < rp.order_domain_items;
+    if (mine && rp.tile_mod > 1) mine = ((item / (rp.groups_per_tile >> 2)) % rp.tile_mod) == rp.tile_rem;  // items never straddle tiles here
+    scene = mine && rp.num_cull_rects > 0 && item_touches_scene(rp, item);
+}
+
+// per block: scene items in the low half, all items of the launch in the high half
 __global__ void __launch_bounds__(kOrderBlock) count_scene_items_kernel(const __grid_constant__ RenderParams rp, int* __restrict__ block_counts)
 {
-    const int item = blockIdx.x * kOrderBlock + threadIdx.x;
-    const bool hit = item < rp.num_items && item_touches_scene(rp, item);
-    const int n = __syncthreads_count(hit);
-    if (threadIdx.x == 0) block_counts[blockIdx.x] = n;
+    bool mine, scene;
+    classify_item(rp, blockIdx.x * kOrderBlock + threadIdx.x, mine, scene);
+    const int ns = __syncthreads_count(scene), nm = __syncthreads_count(mine);
+    if (threadIdx.x == 0) block_counts[blockIdx.x] = ns | (nm << 16);
 }
 
 __global__ void __launch_bounds__(kOrderBlock) place_items_kernel(const __grid_constant__ RenderParams rp, const int* __restrict__ block_counts,
                                                                   int* __restrict__ order)
 {
-    __shared__ int warp_count[kOrderBlock / 32];
-    __shared__ int before_block;
+    __shared__ int warp_a[kOrderBlock / 32], warp_b[kOrderBlock / 32], warp_c[kOrderBlock / 32];
+    __shared__ int s_scene_before, s_sky_before, s_scene_total;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // scene items of the blocks before this one
-    int part = 0;
-    for (int b = tid; b < (int)blockIdx.x; b += kOrderBlock) part += block_counts[b];
-    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
-    if (lane == 0) warp_count[warp] = part;
+    // scene / sky items of the blocks before this one, and the scene items of the whole launch
+    int sb = 0, kb = 0, st = 0;
+    for (int b = tid; b < (int)gridDim.x; b += kOrderBlock) {
+        const int v = block_counts[b], ns = v & 0xffff, nm = v >> 16;
+        st += ns;
+        if (b < (int)blockIdx.x) { sb += ns; kb += nm - ns; }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        sb += __shfl_xor_sync(0xffffffffu, sb, o);
+        kb += __shfl_xor_sync(0xffffffffu, kb, o);
+        st += __shfl_xor_sync(0xffffffffu, st, o);
+    }
+    if (lane == 0) { warp_a[warp] = sb; warp_b[warp] = kb; warp_c[warp] = st; }
     __syncthreads();
     if (tid == 0) {
-        int t = 0;
-        for (int w = 0; w < kOrderBlock / 32; w++) t += warp_count[w];
-        before_block = t;
+        int a = 0, b = 0, c = 0;
+        for (int w = 0; w < kOrderBlock / 32; w++) { a += warp_a[w]; b += warp_b[w]; c += warp_c[w]; }
+        s_scene_before = a; s_sky_before = b; s_scene_total = c;
     }
     __syncthreads();
-    const int scene_before = before_block, first = blockIdx.x * kOrderBlock;
-    const int sky_before = first - scene_before;
-    const int item = first + tid;
-    const bool valid = item < rp.num_items, hit = valid && item_touches_scene(rp, item);
-    const unsigned bt = __ballot_sync(0xffffffffu, hit), bs = __ballot_sync(0xffffffffu, valid && !hit);
+    const int item = blockIdx.x * kOrderBlock + tid;
+    bool mine, scene;
+    classify_item(rp, item, mine, scene);
+    const unsigned bt = __ballot_sync(0xffffffffu, scene), bs = __ballot_sync(0xffffffffu, mine && !scene);
     __syncthreads();
-    if (lane == 0) warp_count[warp] = __popc(bt) | (__popc(bs) << 16);
+    if (lane == 0) warp_a[warp] = __popc(bt) | (__popc(bs) << 16);
     __syncthreads();
     int before_t = 0, before_s = 0;
     for (int w = 0; w < warp; w++) {
-        before_t += warp_count[w] & 0xffff;
-        before_s += warp_count[w] >> 16;
+        before_t += warp_a[w] & 0xffff;
+        before_s += warp_a[w] >> 16;
     }
     const unsigned lt = (1u << lane) - 1u;
-    if (hit) order[scene_before + before_t + __popc(bt & lt)] = item;
-    else if (valid) order[rp.num_items - 1 - (sky_before + before_s + __popc(bs & lt))] = item;
+    if (scene) order[s_scene_before + before_t + __popc(bt & lt)] = item;
+    else if (mine) order[s_scene_total + s_sky_before + before_s + __popc(bs & lt)] = item;
 }
 
-// `order` holds num_items ints followed by ceil(num_items / 1024) ints of scratch
+// `order` holds num_items ints followed by ceil(order_domain_items / 1024) ints of scratch
 cudaError_t launch_build_item_order(const RenderParams& rp, int* order, cudaStream_t stream)
 {
-    const int blocks = (rp.num_items + kOrderBlock - 1) / kOrderBlock;
+    const int blocks = (rp.order_domain_items + kOrderBlock - 1) / kOrderBlock;
     int* counts = order + rp.num_items;
     count_scene_items_kernel<<<blocks, kOrderBlock, 0, stream>>>(rp, counts);
     place_items_kernel<<<blocks, kOrderBlock, 0, stream>>>(rp, counts, order);
+    return cudaGetLastError();
+}
+
+// One rank's tiles of a tile-strided render (FlatTileIndex % mod == rem) copied into another buffer -- rank 0's, over
+// NVLink peer memory: the gather of b200pt_group's tile sharding in one launch per rank.  16 B in, 16 B out per float4.
+__global__ void tile_gather_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int num_tiles, int mod, int rem, int quads_per_tile)
+{
+    const int my_tiles = (num_tiles - rem + mod - 1) / mod;
+    const size_t total = (size_t)my_tiles * quads_per_tile, stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t k = (size_t)blockIdx.x * blockDim.x + threadIdx.x; k < total; k += stride) {
+        const size_t j = k / quads_per_tile, q = k - j * quads_per_tile;
+        const size_t i = ((size_t)rem + j * mod) * quads_per_tile + q;
+        dst[i] = __ldg(src + i);
+    }
+}
+
+cudaError_t launch_tile_gather(const float* src, float* dst, int num_tiles, int mod, int rem, size_t floats_per_tile, int sm_count, cudaStream_t stream)
+{
+    if (floats_per_tile % 4) return cudaErrorInvalidValue;
+    tile_gather_kernel<<<sm_count * 8, 256, 0, stream>>>(reinterpret_cast<const float4*>(src), reinterpret_cast<float4*>(dst), num_tiles, mod, rem,
+                                                         (int)(floats_per_tile / 4));
     return cudaGetLastError();
 }
 

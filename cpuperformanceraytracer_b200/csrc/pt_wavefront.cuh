@@ -34,7 +34,7 @@ constexpr int kWfRecordQuads = 5;   // a path record = 5 x 16 bytes: pos dir thr
 constexpr int kCulledFramesPerTrip = 3;  // a camera-culled pixel never traces: its paths are folded several per trip
 
 template <int PROFILE> struct WfShared {
-    static constexpr int kFields = (PROFILE == kProfileV4 || PROFILE == kProfileV3Redo) ? kV4MatFields : kLegacyMatFields;
+    static constexpr int kFields = (PROFILE == kProfileV4 || is_v3redo(PROFILE)) ? kV4MatFields : kLegacyMatFields;
     float smat[kFields * kMatStride];
     typename SharedOf<PROFILE>::type trace;  // Cornell-family trace: variant table + per-thread candidate stacks
     uint4 rec[kWfRecordQuads][kWfThreads];     // the sort's transit records (128-bit accesses, consecutive threads)
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(kWfThreads, MinBlocks<PROFILE>::value)
 pt_render_sorted_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ typename SceneOf<PROFILE>::type scene)
 {
     constexpr int kFields = WfShared<PROFILE>::kFields;
-    constexpr int kObjects = (PROFILE == kProfileV4) ? kV4MaxObjects : (PROFILE == kProfileV3Redo ? kV3Objects : kCornellObjects);
+    constexpr int kObjects = (PROFILE == kProfileV4) ? kV4MaxObjects : (PROFILE == kProfileV3Redo ? kV3Objects : (PROFILE == kProfileV3RedoS0 ? kV3S0Objects : kCornellObjects));
     extern __shared__ __align__(16) unsigned char wf_raw[];
     WfShared<PROFILE>& S = *reinterpret_cast<WfShared<PROFILE>*>(wf_raw);
     for (int i = threadIdx.x; i < kFields * kMatStride; i += blockDim.x) {
@@ -281,6 +281,10 @@ inline cudaError_t dispatch_config_sorted(const LaunchConfig& lc, F&& f)
         if (lc.static_scene) { B200PT_CASE(kProfileV3Redo, kEnvEquirect, kSamplerBilinear, true) }
         B200PT_CASE(kProfileV3Redo, kEnvEquirect, kSamplerBilinear, false)
     }
+    if (lc.profile == kProfileV3RedoS0) {
+        if (lc.static_scene) { B200PT_CASE(kProfileV3RedoS0, kEnvEquirect, kSamplerBilinear, true) }
+        B200PT_CASE(kProfileV3RedoS0, kEnvEquirect, kSamplerBilinear, false)
+    }
     if (lc.profile == kProfileV4) {
 #define B200PT_V4CASE(EK, ES)                                   \
     if (lc.static_scene) { B200PT_CASE(kProfileV4, EK, ES, true) } \
@@ -307,6 +311,8 @@ inline cudaError_t launch_sorted(const LaunchConfig& lc, const RenderParams& rp,
             kernel<<<lc.grid, kWfThreads, smem, stream>>>(rp, scenes.v4);
         } else if constexpr (std::is_same<KernelT, void (*)(RenderParams, V3RedoScene)>::value) {
             kernel<<<lc.grid, kWfThreads, smem, stream>>>(rp, scenes.v3redo);
+        } else if constexpr (std::is_same<KernelT, void (*)(RenderParams, V3RedoScene0)>::value) {
+            kernel<<<lc.grid, kWfThreads, smem, stream>>>(rp, scenes.v3redo0);
         } else {
             kernel<<<lc.grid, kWfThreads, smem, stream>>>(rp, scenes.cornell);
         }

@@ -12,8 +12,8 @@
 namespace {
 
 B200RenderOptions g_options;
-b200pt_context* g_ctx[4] = {nullptr, nullptr, nullptr, nullptr};  // one per reference translation unit
-b200pt_group* g_group[4] = {nullptr, nullptr, nullptr, nullptr};  // num_gpus > 1: the same, sharded over GPUs
+b200pt_context* g_ctx[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // one per reference translation unit (v3_redo: one per SCENE)
+b200pt_group* g_group[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // num_gpus > 1: the same, sharded over GPUs
 bool g_tile_data_changed = true;                         // tileDataChanged, v4.cpp:1348
 
 [[noreturn]] void die(const char* what, b200pt_context* ctx, int rc)
@@ -30,7 +30,8 @@ b200pt_params params_for(int profile)
     if (rc != B200PT_OK) die("b200pt_default_params", nullptr, rc);
     p.device = g_options.device;
     p.math_mode = g_options.math_mode;
-    p.num_bounces = (profile == B200PT_PROFILE_OPT_V4 || profile == B200PT_PROFILE_V3_REDO) ? g_options.v4_num_bounces : g_options.v2_num_bounces;
+    p.num_bounces = (profile == B200PT_PROFILE_OPT_V4 || profile == B200PT_PROFILE_V3_REDO || profile == B200PT_PROFILE_V3_REDO_SCENE0)
+                        ? g_options.v4_num_bounces : g_options.v2_num_bounces;
     if (profile == B200PT_PROFILE_OPT_V4) {
         p.env_kind = !g_options.use_env_map ? B200PT_ENV_NONE : (g_options.use_env_cubemap ? B200PT_ENV_CUBEMAP : B200PT_ENV_EQUIRECT);
         p.env_sampler = g_options.use_random_jitter_texture_sampling ? B200PT_SAMPLER_RANDOM : B200PT_SAMPLER_BILINEAR;
@@ -128,13 +129,15 @@ void DemofoxRenderSimtTexturedFrames(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 
 
 void DemofoxRenderV3Redo(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture)
 {
-    render(B200PT_PROFILE_V3_REDO, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, 1);
+    render(g_options.v3_redo_scene == 0 ? B200PT_PROFILE_V3_REDO_SCENE0 : B200PT_PROFILE_V3_REDO, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels,
+           Texture, nullptr, 1);
 }
 
 void DemofoxRenderV3RedoFrames(f32* BufferOut, i32 W, i32 H, i32 NTX, i32 NTY, i32 TW, i32 TH, i32 NumChannels, texture Texture,
                                i32 NumFrames)
 {
-    render(B200PT_PROFILE_V3_REDO, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels, Texture, nullptr, NumFrames);
+    render(g_options.v3_redo_scene == 0 ? B200PT_PROFILE_V3_REDO_SCENE0 : B200PT_PROFILE_V3_REDO, BufferOut, W, H, NTX, NTY, TW, TH, NumChannels,
+           Texture, nullptr, NumFrames);
 }
 
 // CopyOutputToFile (v4.cpp:1729-1760): tone-maps the f32 buffer into ScreenBufferData
@@ -199,7 +202,8 @@ void WriteImage(char* filename, i32 width, i32 height, i32 components, void* dat
 B200RenderStats B200GetRenderStats(int variant)
 {
     B200RenderStats s{};
-    if (variant < 0 || variant > 3 || (!g_ctx[variant] && !g_group[variant])) return s;
+    if (variant == 3 && g_options.v3_redo_scene == 0) variant = 4;
+    if (variant < 0 || variant > 4 || (!g_ctx[variant] && !g_group[variant])) return s;
     b200pt_counters c;
     if (g_group[variant] ? b200pt_group_get_counters(g_group[variant], &c, &s.combine_ms) == B200PT_OK
                          : b200pt_get_counters(g_ctx[variant], &c) == B200PT_OK) {

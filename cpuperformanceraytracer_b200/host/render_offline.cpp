@@ -4,7 +4,7 @@
 // ms/frame (:444-452), tone-map and write output_image.bmp (PostprocessAndWriteImageToFile, :381-398).
 // It is written against the reference's own entry-point names (demofox_render.h).
 //
-//   render_offline [--variant v4|v2|simt|v3redo] [--width W --height H --tiles-x X --tiles-y Y]
+//   render_offline [--variant v4|v2|simt|v3redo|v3redo0] [--width W --height H --tiles-x X --tiles-y Y]
 //                  [--frames N] [--bounces B] [--env file.hdr | --cubemap px nx py ny pz nz]
 //                  [--bilinear] [--fast] [--per-frame-calls] [--out out.bmp] [--dump-f32 file]
 //                  [--gpus N [--shard spp|tiles] [--combine nccl|peer]] [--device D]
@@ -57,10 +57,14 @@ int main(int argc, char** argv)
     texture Texture;
     if (cube[0]) Texture = LoadCubemapTexture(cube);
     else if (!env_path.empty()) Texture = LoadTexture((char*)env_path.c_str());
-    const bool needs_env = (variant == "simt") || (variant == "v4") || (variant == "v3redo");
+    const bool needs_env = (variant == "simt") || (variant == "v4") || (variant == "v3redo") || (variant == "v3redo0");
     if (needs_env && !Texture.Data) {
         if (variant == "v4") opt.use_env_map = 0;  // no texture given: constant ambient
         else { std::fprintf(stderr, "--variant %s needs --env file.hdr\n", variant.c_str()); return 2; }
+    }
+    if (variant == "v3redo0") {  // demofox_path_tracing_v3_redo.cpp with `#define SCENE 0`
+        opt.v3_redo_scene = 0;
+        variant = "v3redo";
     }
     B200SetRenderOptions(opt);
 

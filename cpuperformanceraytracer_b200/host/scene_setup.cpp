@@ -194,6 +194,36 @@ void build_v3redo_scene(V3RedoScene* s)
     s->cameraPosition = mk(0.f, 0.f, 1.f * 40.f);  // :796
 }
 
+// Scene of demofox_path_tracing_v3_redo.cpp compiled with SCENE 0 (:392-479 walls, :530-543 light, :545-580 spheres)
+void build_v3redo_scene0(V3RedoScene0* s)
+{
+    std::memset(s, 0, sizeof(*s));
+    const v3 T = mk(0.0f, 0.0f, 0.0f);  // sceneTranslation, :387
+    for (int i = 0; i < kV3S0Quads; i++) {
+        LegacyQuad& q = s->quad[i];
+        v3* dst[4] = {&q.a, &q.b, &q.c, &q.d};
+        for (int k = 0; k < 4; k++) *dst[k] = add(mk(kV3S0QuadVerts[i][k][0], kV3S0QuadVerts[i][k][1], kV3S0QuadVerts[i][k][2]), T);
+        q.n = normalize(cross(sub(q.c, q.a), sub(q.c, q.b)));  // :225
+    }
+    for (int i = 0; i < kV3S0Objects; i++) s->mat[i].IOR = 1.f;  // GetZeroedMaterial, :155-168
+    s->mat[0].albedo = mk(0.7f, 0.7f, 0.7f);
+    s->mat[1].albedo = mk(0.7f, 0.7f, 0.7f);
+    s->mat[2].albedo = mk(0.7f, 0.7f, 0.7f);
+    s->mat[3].albedo = mk(0.7f, 0.1f, 0.1f);
+    s->mat[4].albedo = mk(0.1f, 0.7f, 0.1f);
+    s->mat[5].emissive = muls(mk(1.0f, 0.9f, 0.7f), 20.0f);
+    const float cx[3] = {-9.0f, 0.0f, 9.0f};
+    for (int i = 0; i < kV3S0Spheres; i++) {
+        const v3 c = add(mk(cx[i], -9.5f, 20.0f), T);
+        s->sphere[i] = make_float4(c.x, c.y, c.z, 3.0f + 0.0f);
+    }
+    V4Material* m = &s->mat[kV3S0Quads];
+    m[0].albedo = mk(0.9f, 0.9f, 0.5f); m[0].specularChance = 0.1f; m[0].specularRoughness = 0.2f; m[0].specularColor = mk(0.9f, 0.9f, 0.9f);
+    m[1].albedo = mk(0.9f, 0.5f, 0.9f); m[1].specularChance = 0.3f; m[1].specularRoughness = 0.2f; m[1].specularColor = mk(0.9f, 0.9f, 0.9f);
+    m[2].albedo = mk(0.f, 0.f, 1.f);    m[2].specularChance = 0.5f; m[2].specularRoughness = 0.4f; m[2].specularColor = mk(1.f, 0.f, 0.f);
+    s->cameraPosition = mk(0.f, 0.f, 1.f * 40.f);  // :796
+}
+
 // ---- camera-ray culling ---------------------------------------------------------------------------
 // A camera ray through fragCoord (fx, fy) has direction (tx, ty / aspect, camDist) with
 // tx = fx / W * 2 - 1, ty = fy / H * 2 - 1 from the origin (v2.cpp:543-560), or
@@ -298,6 +328,19 @@ int compute_cull_rects(int profile, int width, int height, float4* rects)
         }
         for (int i = 0; i < kV4Spheres; i++)
             if (!project_box(sphere_box(s.sphere[i]), kProfileV4, width, height, camDist, &rects[n++])) return -1;
+    } else if (profile == kProfileV3RedoS0) {  // the box (walls enclose the spheres) and the light far behind it, seen from (0, 0, 40)
+        V3RedoScene0 s;
+        build_v3redo_scene0(&s);
+        Box b = empty_box();
+        for (int i = 0; i < kV3S0Quads - 1; i++) { grow(&b, s.quad[i].a); grow(&b, s.quad[i].b); grow(&b, s.quad[i].c); grow(&b, s.quad[i].d); }
+        for (int i = 0; i < kV3S0Spheres; i++) { const Box sb = sphere_box(s.sphere[i]); grow(&b, mk((float)sb.lo[0], (float)sb.lo[1], (float)sb.lo[2])); grow(&b, mk((float)sb.hi[0], (float)sb.hi[1], (float)sb.hi[2])); }
+        for (int a = 0; a < 3; a++) { b.lo[a] -= 1e-3; b.hi[a] += 1e-3; }
+        if (!project_box(b, kProfileV4, width, height, camDist, &rects[n++])) return -1;
+        Box l = empty_box();
+        const LegacyQuad& L = s.quad[kV3S0Quads - 1];
+        grow(&l, L.a); grow(&l, L.b); grow(&l, L.c); grow(&l, L.d);
+        for (int a = 0; a < 3; a++) { l.lo[a] -= 1e-3; l.hi[a] += 1e-3; }
+        if (!project_box(l, kProfileV4, width, height, camDist, &rects[n++])) return -1;
     } else {
         CornellScene s;
         build_cornell_scene(&s, profile == kProfileSimtTextured);

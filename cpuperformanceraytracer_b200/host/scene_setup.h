@@ -7,6 +7,7 @@ float camera_distance();
 void build_cornell_scene(CornellScene* s, bool simt_textured_materials);
 void build_v4_scene(V4Scene* s);
 void build_v3redo_scene(V3RedoScene* s);
+void build_v3redo_scene0(V3RedoScene0* s);
 // AddQuadObjectToScene / AddSphereObjectToScene / AddMaterialToScene (v4.cpp:1368-1401) on caller data:
 // quads as 4 vertices (12 floats each), spheres as xyz + radius, materials in the 17-float order of
 // SceneMaterial (v4.cpp:351-362); like AddMaterialToScene, albedo.y / albedo.z are replaced by albedo.x.

@@ -43,9 +43,12 @@ enum {
                                          diffuse/emissive, equirect point-sampled env) */
     B200PT_PROFILE_OPT_V4 = 2,        /* DemofoxRenderOptV4, ..._optimization_v4.cpp:1696 (7 spheres,
                                          Fresnel/refraction/absorption, equirect or cubemap env) */
-    B200PT_PROFILE_V3_REDO = 3        /* DemofoxRenderV3Redo, demofox_path_tracing_v3_redo.cpp:886, SCENE 1: the v4
+    B200PT_PROFILE_V3_REDO = 3,       /* DemofoxRenderV3Redo, demofox_path_tracing_v3_redo.cpp:886, SCENE 1: the v4
                                          scene and shading without the approximations (exact divisions, exp(),
                                          sin/cos unit vectors, striped backdrop), bilinear equirect env, 8 bounces */
+    B200PT_PROFILE_V3_REDO_SCENE0 = 4 /* the same renderer compiled with `#define SCENE 0` (v3_redo.cpp:379, :392-479,
+                                         :530-580): the Cornell box seen from (0, 0, 40), three Fresnel-specular
+                                         spheres, the light outside the box */
 };
 
 /* arithmetic policy */
@@ -229,6 +232,10 @@ int b200pt_set_tile_row_range(b200pt_context* ctx, int32_t first_tile_row, int32
  * render calls to the tiles FlatTileIndex in [first, first + count), FlatTileIndex = TileX + NumTilesX *
  * TileY.  Consecutive flat indices are contiguous in the buffer.  (0, 0) = all tiles. */
 int b200pt_set_tile_range(b200pt_context* ctx, int32_t first_flat_tile, int32_t num_tiles);
+/* ... or to every modulus-th tile: FlatTileIndex % modulus == remainder (tiles of N ranks interleave over the image, which
+ * balances cheap sky tiles and expensive scene tiles without a cost model).  Needs tiles of a multiple of 32 pixels.
+ * (0, 0) or modulus 1 = all tiles.  Replaces a tile range and vice versa. */
+int b200pt_set_tile_stride(b200pt_context* ctx, int32_t remainder, int32_t modulus);
 /* ACCUM_SUM epilogue: target *= 1/(total_frames + 1), the value the reference's running average
  * reaches after render calls 1..total_frames on a zeroed buffer.  total_frames is
  * the LAST frame index of the job, not the number of frames of one shard. */

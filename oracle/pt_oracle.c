@@ -565,29 +565,61 @@ static v3 RandomUnitVectorRejectionSample(uint32_t* state)
     return muls(V3(u, v, w), rsroot_exact(uvw_d2));
 }
 
-/* ---- v3_redo, SCENE 1: v3_redo.cpp:195-219 (Fresnel), :485-600 (scene), :607-754 (shading) ---- */
+/* ---- v3_redo: v3_redo.cpp:195-219 (Fresnel), :379-602 (scenes: SCENE 1 = the v4 geometry, the checked-in choice;
+ * ---- SCENE 0 = a Cornell box with Fresnel-specular spheres and a light outside the box), :607-754 (shading) ---- */
 typedef struct {
-    v3 quad[4][4];
+    int nquads, nspheres;
+    int backdrop;          /* index of the striped backdrop quad (albedo computed at the hit), -1: none */
+    v3 quad[6][4];
     v3 sphereCenter[7];
     float sphereRadius[7];
-    mat4_t mat[11]; /* [1] (striped backdrop) albedo is computed at the hit */
+    mat4_t mat[13];        /* quads first, then spheres */
 } scene3_t;
 
-static void scene3_init(scene3_t* s)
+static void scene3_init(scene3_t* s, int scene)
 {
-    const v3 T = V3(0.0f, 0.0f, 10.0f);
     memset(s, 0, sizeof(*s));
+    for (int i = 0; i < 13; i++) s->mat[i].IOR = 1.f; /* GetZeroedMaterial, :155-168 */
+    if (scene == 0) { /* :392-479, :530-580; sceneTranslation = 0 (:387) */
+        const v3 T = V3(0.0f, 0.0f, 0.0f);
+        static const float Q[6][4][3] = {
+            {{-12.6f, -12.6f, 25.0f}, {12.6f, -12.6f, 25.0f}, {12.6f, 12.6f, 25.0f}, {-12.6f, 12.6f, 25.0f}},        /* back wall */
+            {{-12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 25.0f}, {12.6f, -12.45f, 15.0f}, {-12.6f, -12.45f, 15.0f}},  /* floor */
+            {{-12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 25.0f}, {12.6f, 12.5f, 15.0f}, {-12.6f, 12.5f, 15.0f}},          /* ceiling */
+            {{-12.5f, -12.6f, 25.0f}, {-12.5f, -12.6f, 15.0f}, {-12.5f, 12.6f, 15.0f}, {-12.5f, 12.6f, 25.0f}},      /* left wall */
+            {{12.5f, -12.6f, 25.0f}, {12.5f, -12.6f, 15.0f}, {12.5f, 12.6f, 15.0f}, {12.5f, 12.6f, 25.0f}},          /* right wall */
+            {{-5.0f, 12.4f, -22.5f}, {5.0f, 12.4f, -22.5f}, {5.0f, 12.4f, -17.5f}, {-5.0f, 12.4f, -17.5f}}};         /* light */
+        s->nquads = 6; s->nspheres = 3; s->backdrop = -1;
+        for (int i = 0; i < 6; i++)
+            for (int k = 0; k < 4; k++) s->quad[i][k] = add3(V3(Q[i][k][0], Q[i][k][1], Q[i][k][2]), T);
+        s->mat[0].albedo = V3(0.7f, 0.7f, 0.7f);
+        s->mat[1].albedo = V3(0.7f, 0.7f, 0.7f);
+        s->mat[2].albedo = V3(0.7f, 0.7f, 0.7f);
+        s->mat[3].albedo = V3(0.7f, 0.1f, 0.1f);
+        s->mat[4].albedo = V3(0.1f, 0.7f, 0.1f);
+        s->mat[5].emissive = muls(V3(1.0f, 0.9f, 0.7f), 20.0f);
+        static const float C[3] = {-9.0f, 0.0f, 9.0f};
+        for (int i = 0; i < 3; i++) {
+            s->sphereCenter[i] = add3(V3(C[i], -9.5f, 20.0f), T);
+            s->sphereRadius[i] = 3.0f + 0.0f;
+        }
+        s->mat[6].albedo = V3(0.9f, 0.9f, 0.5f); s->mat[6].specularChance = 0.1f; s->mat[6].specularRoughness = 0.2f; s->mat[6].specularColor = V3(0.9f, 0.9f, 0.9f);
+        s->mat[7].albedo = V3(0.9f, 0.5f, 0.9f); s->mat[7].specularChance = 0.3f; s->mat[7].specularRoughness = 0.2f; s->mat[7].specularColor = V3(0.9f, 0.9f, 0.9f);
+        s->mat[8].albedo = V3(0.f, 0.f, 1.f);    s->mat[8].specularChance = 0.5f; s->mat[8].specularRoughness = 0.4f; s->mat[8].specularColor = V3(1.f, 0.f, 0.f);
+        return;
+    }
+    const v3 T = V3(0.0f, 0.0f, 10.0f);
     static const float Q[4][4][3] = {
         {{-25.0f, -12.5f, 5.0f}, {25.0f, -12.5f, 5.0f}, {25.0f, -12.5f, -5.0f}, {-25.0f, -12.5f, -5.0f}},
         {{-25.0f, -1.5f, 5.0f}, {25.0f, -1.5f, 5.0f}, {25.0f, -10.5f, 5.0f}, {-25.0f, -10.5f, 5.0f}},
         {{-7.5f, 12.5f, 5.0f}, {7.5f, 12.5f, 5.0f}, {7.5f, 12.5f, -5.0f}, {-7.5f, 12.5f, -5.0f}},
         {{-5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, 2.5f}, {5.0f, 12.4f, -2.5f}, {-5.0f, 12.4f, -2.5f}}};
+    s->nquads = 4; s->nspheres = 7; s->backdrop = 1;
     for (int i = 0; i < 4; i++)
         for (int k = 0; k < 4; k++) {
             v3 p = V3(Q[i][k][0], Q[i][k][1], Q[i][k][2]);
             s->quad[i][k] = (i == 1) ? p : add3(p, T); /* the backdrop is not translated, :505-508 */
         }
-    for (int i = 0; i < 11; i++) s->mat[i].IOR = 1.f; /* GetZeroedMaterial, :155-168 */
     s->mat[0].albedo = V3(0.7f, 0.7f, 0.7f);
     s->mat[2].albedo = V3(0.7f, 0.7f, 0.7f);
     s->mat[3].emissive = muls(V3(1.0f, 0.9f, 0.7f), 20.0f);
@@ -785,6 +817,8 @@ static float FresnelReflectAmount_v3(float n1, float n2, v3 normal, v3 incident,
     return f0 + ret * (f90 - f0);
 }
 
+#define IS_V3REDO(profile) ((profile) == ORACLE_PROFILE_V3REDO || (profile) == ORACLE_PROFILE_V3REDO_SCENE0)
+
 static v3 GetColorForRay_v3redo(const scene3_t* s, const oracle_params* p, const tex_t* tex, v3 rayPos, v3 rayDir,
                                 uint32_t* rng, path_stats_t* st)
 {
@@ -794,17 +828,17 @@ static v3 GetColorForRay_v3redo(const scene3_t* s, const oracle_params* p, const
         h.fromInside = 0; h.dist = c_superFar; h.normal = V3(0.f, 0.f, 0.f); h.matIndex = -1;
         v3 backdropAlbedo = V3(0.f, 0.f, 0.f);
         st->segments++;
-        for (int i = 0; i < 4; i++)
+        for (int i = 0; i < s->nquads; i++)
             if (TestQuadTrace_legacy(rayPos, rayDir, &h, s->quad[i][0], s->quad[i][1], s->quad[i][2], s->quad[i][3])) {
                 h.matIndex = i;
-                if (i == 1) { /* striped backdrop, :511-515 */
+                if (i == s->backdrop) { /* striped backdrop, :511-515 */
                     v3 hitPos = add3(rayPos, muls(rayDir, h.dist));
                     float shade = floorf(fract1(hitPos.x) * 2.0f);
                     backdropAlbedo = V3(shade, shade, shade);
                 }
             }
-        for (int i = 0; i < 7; i++)
-            if (TestSphereTrace_legacy(rayPos, rayDir, &h, s->sphereCenter[i], s->sphereRadius[i])) h.matIndex = 4 + i;
+        for (int i = 0; i < s->nspheres; i++)
+            if (TestSphereTrace_legacy(rayPos, rayDir, &h, s->sphereCenter[i], s->sphereRadius[i])) h.matIndex = s->nquads + i;
         if (h.dist == c_superFar) {
             v3 SampleDir = V3(-rayDir.x, rayDir.y, -rayDir.z);
             v3 ambient = mul3(EquirectSampleBilinear(tex, SampleDir), throughput);
@@ -812,7 +846,7 @@ static v3 GetColorForRay_v3redo(const scene3_t* s, const oracle_params* p, const
             return add3(ret, ambient);
         }
         mat4_t m = s->mat[h.matIndex];
-        if (h.matIndex == 1) m.albedo = backdropAlbedo;
+        if (h.matIndex == s->backdrop) m.albedo = backdropAlbedo;
         if (h.fromInside) {
             throughput.x = throughput.x * pm_expf(-m.refractionColor.x * h.dist);
             throughput.y = throughput.y * pm_expf(-m.refractionColor.y * h.dist);
@@ -888,7 +922,7 @@ static v3 mainImage(const ctx_t* c, int x, int yflip, int frame, uint32_t* rng_o
     } else {
         float cameraDistance = oracle_camera_distance();
         float tx, ty;
-        if (p->profile == ORACLE_PROFILE_V2 || p->profile == ORACLE_PROFILE_V3REDO) {
+        if (p->profile == ORACLE_PROFILE_V2 || IS_V3REDO(p->profile)) {
             float jx = RAND01(&rng) - .5f;
             float jy = RAND01(&rng) - .5f;
             tx = ((fx + jx) / resx) * 2.0f - 1.f;
@@ -903,7 +937,7 @@ static v3 mainImage(const ctx_t* c, int x, int yflip, int frame, uint32_t* rng_o
         v3 rayPosition = V3(0.f, 0.f, 0.f);
         v3 rayDir = normalize3(sub3(rayTarget, rayPosition));
         v3 col;
-        if (p->profile == ORACLE_PROFILE_V3REDO) { /* v3_redo.cpp:791-798: camera at (0,0,40) looking down -z */
+        if (IS_V3REDO(p->profile)) { /* v3_redo.cpp:791-798: camera at (0,0,40) looking down -z */
             rayDir.z = rayDir.z * -1.f;
             col = GetColorForRay_v3redo(&c->scene3, p, &c->tex, V3(0.f, 0.f, 1.f * 40.f), rayDir, &rng, st);
         } else
@@ -919,15 +953,15 @@ static int ctx_init(ctx_t* c, const oracle_params* p)
 {
     if (!p || p->width <= 0 || p->height <= 0 || p->num_tiles_x <= 0 || p->num_tiles_y <= 0) return -1;
     if (p->width % p->num_tiles_x || p->height % p->num_tiles_y || (p->width / p->num_tiles_x) % 8) return -1;
-    if (p->profile < 0 || p->profile > 3 || p->num_bounces < 0) return -1;
-    int needs_env = (p->profile == ORACLE_PROFILE_SIMT_TEXTURED) || (p->profile == ORACLE_PROFILE_V3REDO) ||
+    if (p->profile < 0 || p->profile > 4 || p->num_bounces < 0) return -1;
+    int needs_env = (p->profile == ORACLE_PROFILE_SIMT_TEXTURED) || IS_V3REDO(p->profile) ||
                     (p->profile == ORACLE_PROFILE_V4 && p->env_kind != ORACLE_ENV_NONE);
     if (needs_env && (!p->env || p->env_width <= 0 || p->env_height <= 0)) return -1;
     c->p = p;
     cornell_init(&c->cornell, p->profile);
     scene4_init(&c->scene4);
     if (p->profile == ORACLE_PROFILE_V4 && p->scene_v4 && scene4_from(&c->scene4, p->scene_v4)) return -1;
-    scene3_init(&c->scene3);
+    scene3_init(&c->scene3, p->profile == ORACLE_PROFILE_V3REDO_SCENE0 ? 0 : 1);
     c->tex.data = p->env; c->tex.W = p->env_width; c->tex.H = p->env_height;
     return 0;
 }

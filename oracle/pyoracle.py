@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "liboracle.so")
 REF_DIR = os.path.join(HERE, "_ref")
 
-PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_V4, PROFILE_V3REDO = 0, 1, 2, 3
+PROFILE_V2, PROFILE_SIMT_TEXTURED, PROFILE_V4, PROFILE_V3REDO, PROFILE_V3REDO_SCENE0 = 0, 1, 2, 3, 4
 ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
 SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
 

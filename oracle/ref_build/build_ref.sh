@@ -6,6 +6,8 @@
 #   * "const int c_numBounces = N;"  -> "int c_numBounces = N;"      (harness sets --bounces)
 #   * "static f32 iFrame = 0.f;"     -> "f32 iFrame = 0.f;"          (harness sets --start-frame)
 #   * NUM_THREADS                    -> oracle_num_threads            (harness sets --threads)
+#   * v3_redo only: "#define SCENE 1" -> "#ifndef SCENE / #define SCENE 1 / #endif" so that -DSCENE=0 selects the
+#     renderer's other checked-in scene (demofox_path_tracing_v3_redo.cpp:379,392-479,530-580)
 #   * v4 only: the compile-time switches of global_preprocessor_flags.h:56-66 that pick the env
 #     sampler / per-tile screen output are renamed ORACLE_<name> and set with -D, because that
 #     header is found next to the including file and cannot be overridden from outside.
@@ -28,6 +30,7 @@ PATCH=(-E
   -e 's/^const int c_numBounces = ([0-9]+);/int c_numBounces = \1;/'
   -e 's/^static f32 iFrame = 0\.f;/f32 iFrame = 0.f;/'
   -e 's/\bNUM_THREADS\b/oracle_num_threads/g'
+  -e 's/^#define SCENE 1$/#ifndef SCENE\n#define SCENE 1\n#endif/'
   -e 's/^#if USE_ENV_CUBEMAP/#if ORACLE_USE_ENV_CUBEMAP/'
   -e 's/^#if USE_RANDOM_JITTER_TEXTURE_SAMPLING/#if ORACLE_USE_RANDOM_JITTER_TEXTURE_SAMPLING/'
   -e 's/^#if OUTPUT_TO_SCREEN/#if ORACLE_OUTPUT_TO_SCREEN/')
@@ -60,6 +63,7 @@ for mode in exact asis; do
     build_variant "ref_v4_equirect_random_$mode" 3 demofox_path_tracing_optimization_v4.cpp "$mode" $V4_EQ_RAND &
     build_variant "ref_v4_cubemap_random_$mode" 3 demofox_path_tracing_optimization_v4.cpp "$mode" $V4_CUBE_RAND &
     build_variant "ref_v3redo_$mode" 4 demofox_path_tracing_v3_redo.cpp "$mode" &
+    build_variant "ref_v3redo_scene0_$mode" 4 demofox_path_tracing_v3_redo.cpp "$mode" -DSCENE=0 &
     for j in $(jobs -p); do wait "$j"; done
 done
 build_variant ref_v4_equirect_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_BILIN &

@@ -36,6 +36,7 @@ CASES = [
     ("v4_cubemap_bilinear", "ref_v4_cubemap_bilinear_exact", po.PROFILE_V4, po.ENV_CUBEMAP, po.SAMPLER_BILINEAR,
      (32, 192), 128, 72, 4, 6, 8, 6),
     ("v3redo", "ref_v3redo_exact", po.PROFILE_V3REDO, po.ENV_EQUIRECT, po.SAMPLER_BILINEAR, (128, 64), 128, 72, 2, 4, 8, 6),
+    ("v3redo_scene0", "ref_v3redo_scene0_exact", po.PROFILE_V3REDO_SCENE0, po.ENV_EQUIRECT, po.SAMPLER_BILINEAR, (128, 64), 128, 72, 2, 4, 8, 6),
     ("v4_b16", "ref_v4_equirect_random_exact", po.PROFILE_V4, po.ENV_EQUIRECT, po.SAMPLER_RANDOM,
      (128, 64), 64, 40, 2, 5, 16, 4),
 ]

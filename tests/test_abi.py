@@ -35,7 +35,7 @@ def test_built_in_scenes_match_the_specialised_kernels_tables():
     vectors) are what the host builds from the reference's scene expressions -- otherwise the library would silently
     run the slower generic kernels"""
     lib = api.load_library()
-    for profile in (api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_OPT_V4, api.PROFILE_V3_REDO):
+    for profile in (api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_OPT_V4, api.PROFILE_V3_REDO, api.PROFILE_V3_REDO_SCENE0):
         assert lib.b200pt_static_tables_match(profile) == 1
     assert lib.b200pt_static_tables_match(99) == -1
 

@@ -22,11 +22,12 @@ def sure_miss_mask(profile, W, H):
 @pytest.mark.parametrize("profile,oprofile,W,H,frames", [
     (api.PROFILE_V2, 0, 320, 180, 24), (api.PROFILE_V2, 0, 256, 256, 16), (api.PROFILE_V2, 0, 200, 64, 16),
     (api.PROFILE_OPT_V4, 2, 320, 180, 24), (api.PROFILE_OPT_V4, 2, 128, 256, 16), (api.PROFILE_V3_REDO, 3, 320, 180, 16),
+    (api.PROFILE_V3_REDO_SCENE0, 4, 320, 180, 16), (api.PROFILE_V3_REDO_SCENE0, 4, 96, 160, 12),
 ])
 def test_culled_pixels_always_escape_in_the_oracle(oracle, profile, oprofile, W, H, frames):
     mask = sure_miss_mask(profile, W, H)
-    env = oracle.synthetic_env(64, 32) if oprofile == 3 else None
-    seg = oracle.max_segments(oprofile, W, H, 8, frames, env=env, env_kind=1 if oprofile == 3 else 0, env_sampler=1 if oprofile == 3 else 0)
+    env = oracle.synthetic_env(64, 32) if oprofile >= 3 else None
+    seg = oracle.max_segments(oprofile, W, H, 8, frames, env=env, env_kind=1 if oprofile >= 3 else 0, env_sampler=1 if oprofile >= 3 else 0)
     assert (seg[mask] == 1).all(), "a culled pixel hit geometry in the reference arithmetic"
     # usefulness: most pixels that always escape are culled (the bounds are not absurdly loose)
     always_escape = seg == 1

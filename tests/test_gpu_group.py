@@ -114,6 +114,46 @@ def test_spp_shard_group_peer_combine(label, devices):
         assert np.allclose(buf, seq[1], rtol=3e-6, atol=3e-6)
 
 
+def test_tile_shard_group_other_tile_shapes(oracle):
+    """tiles whose area is not a multiple of 32 pixels cannot interleave (work items would straddle tiles): the group falls
+    back to contiguous, cost-balanced tile ranges -- still bit-identical"""
+    w, h, ntx, nty = 72, 15, 3, 5  # tiles of 24 x 3 pixels: 9 SoA8 groups
+    o, _ = oracle.render(0, w, h, ntx, nty, BOUNCES, 9)
+    with api.Group([0, 0, 0], sharding=api.SHARD_TILES, profile=api.PROFILE_V2, num_bounces=BOUNCES) as g:
+        g.resize(w, h, ntx, nty)
+        g.render_frames(4)
+        g.render_frames(5)
+        assert np.array_equal(g.download_target(), o)
+        buf = np.zeros(w * h * 3, dtype=np.float32)
+        g.frame_counter = 0
+        g.render_host(buf, w, h, ntx, nty, 9)
+        assert np.array_equal(buf, o)
+
+
+def test_tile_stride_on_one_context(oracle):
+    """b200pt_set_tile_stride: every modulus-th tile per launch; the residues assemble the full render, bit for bit"""
+    w, h, ntx, nty, frames = 192, 120, 3, 5, 9
+    o, oc = oracle.render(0, w, h, ntx, nty, BOUNCES, frames)
+    for sched in (api.SCHED_LANE, api.SCHED_SORTED):
+        with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES, scheduler=sched) as r:
+            r.resize(w, h, ntx, nty)
+            for mod in (4, 1, 16):
+                r.reset()
+                for rem in range(mod):
+                    r.frame_counter = 0
+                    r.set_tile_stride(rem, mod)
+                    r.render_frames(frames)
+                assert np.array_equal(r.download_target(), o), (sched, mod)
+            r.set_tile_stride(0, 0)
+            with pytest.raises(api.B200PTError):
+                r.set_tile_stride(3, 3)
+        c = None
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES) as r:
+        r.resize(72, 15, 3, 5)
+        with pytest.raises(api.B200PTError, match="32 pixels"):
+            r.set_tile_stride(0, 2)
+
+
 def test_group_with_env_profile(oracle):
     env = oracle.synthetic_env(64, 384)
     seq = _sequential([10], profile=api.PROFILE_OPT_V4, env=env, env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM)[0]

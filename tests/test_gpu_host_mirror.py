@@ -103,6 +103,10 @@ def test_render_offline_simt_and_v3redo(oracle, io, tmp_path):
     o, _ = oracle.render(oracle.PROFILE_V3REDO, W, H, NTX, NTY, 8, FRAMES + 2, env=tex, env_kind=oracle.ENV_EQUIRECT,
                          env_sampler=oracle.SAMPLER_BILINEAR)
     assert np.array_equal(g, o)
+    g, _ = run_cli(tmp_path, "--variant", "v3redo0", "--env", path, name="scene0")   # `#define SCENE 0`
+    o, _ = oracle.render(oracle.PROFILE_V3REDO_SCENE0, W, H, NTX, NTY, 8, FRAMES + 2, env=tex, env_kind=oracle.ENV_EQUIRECT,
+                         env_sampler=oracle.SAMPLER_BILINEAR)
+    assert np.array_equal(g, o)
 
 
 @pytest.mark.skipif(not os.path.isdir(TEX_DIR), reason="the reference's shipped textures are only present in the build container")

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 from cpuperformanceraytracer_b200 import api  # noqa: E402
 
-GPU_PROFILE = {0: api.PROFILE_V2, 1: api.PROFILE_SIMT_TEXTURED, 2: api.PROFILE_OPT_V4, 3: api.PROFILE_V3_REDO}
+GPU_PROFILE = {0: api.PROFILE_V2, 1: api.PROFILE_SIMT_TEXTURED, 2: api.PROFILE_OPT_V4, 3: api.PROFILE_V3_REDO, 4: api.PROFILE_V3_REDO_SCENE0}
 
 
 def make_renderer(case_profile, bounces, env_kind, env_sampler, math_mode=api.MATH_PARITY, **kw):
@@ -50,6 +50,7 @@ CONFIGS = [
     ("v4_cubemap_bilinear", 2, (64, 384), 2, 1, 8),
     ("v4_no_env", 2, None, 0, 0, 8),
     ("v3_redo", 3, (256, 128), 1, 1, 8),
+    ("v3_redo_scene0", 4, (256, 128), 1, 1, 8),
 ]
 
 
@@ -235,8 +236,9 @@ def test_full_size_properties():
 
 @pytest.mark.parametrize("profile,envshape,ek,es", [(api.PROFILE_V2, None, None, None), (api.PROFILE_OPT_V4, (128, 64), 1, 2),
                                                     (api.PROFILE_SIMT_TEXTURED, (128, 64), None, None),
-                                                    (api.PROFILE_V3_REDO, (128, 64), None, None)],
-                         ids=["v2", "v4", "simt_textured", "v3_redo"])
+                                                    (api.PROFILE_V3_REDO, (128, 64), None, None),
+                                                    (api.PROFILE_V3_REDO_SCENE0, (128, 64), None, None)],
+                         ids=["v2", "v4", "simt_textured", "v3_redo", "v3_redo_scene0"])
 def test_camera_culling_changes_nothing(oracle, profile, envshape, ek, es):
     """Skipping the scene trace for pixels whose jitter footprint misses every primitive's screen
     bounds must not change a single bit (buffer, RNG states, counters)."""
@@ -306,8 +308,8 @@ def test_tile_row_bands_assemble_to_the_full_render(oracle):
         assert np.array_equal(r.download_target(), o)
 
 
-@pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_V3_REDO, api.PROFILE_OPT_V4],
-                         ids=["v2", "simt_textured", "v3_redo", "opt_v4"])
+@pytest.mark.parametrize("profile", [api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_V3_REDO, api.PROFILE_OPT_V4, api.PROFILE_V3_REDO_SCENE0],
+                         ids=["v2", "simt_textured", "v3_redo", "opt_v4", "v3_redo_scene0"])
 def test_static_scene_specialisation_changes_nothing(oracle, profile):
     """Built-in scene as compile-time knowledge (default: quad vertices / sphere centres as immediates, zero
     components of the v4 quad tables dropped, unchecked reciprocals for the built-in materials) vs the generic

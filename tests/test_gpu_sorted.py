@@ -50,6 +50,7 @@ def test_sorted_equals_lane_scheduler_everywhere(oracle):
         dict(profile=api.PROFILE_OPT_V4, num_bounces=8, env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM, output_to_screen=True),
         dict(profile=api.PROFILE_OPT_V4, num_bounces=3, env_kind=api.ENV_NONE, generic_scene_tables=True),
         dict(profile=api.PROFILE_SIMT_TEXTURED, num_bounces=4), dict(profile=api.PROFILE_V3_REDO, num_bounces=8),
+        dict(profile=api.PROFILE_V3_REDO_SCENE0, num_bounces=5),
     ]
     sizes = [(8, 1, 1, 1), (24, 5, 3, 5), (40, 3, 1, 3), (320, 200, 4, 5), (264, 130, 3, 2)]
     for kw in cases:

@@ -56,6 +56,24 @@ def test_v3_redo(oracle, bounces, frames, tiles):
 
 
 @needs_ref
+@pytest.mark.parametrize("bounces,frames,tiles", [(8, 4, (2, 4)), (3, 3, (4, 3))])
+def test_v3_redo_scene0(oracle, bounces, frames, tiles):
+    """demofox_path_tracing_v3_redo.cpp compiled with `#define SCENE 0` (the Cornell box variant, :392-479, :530-580)"""
+    if not po.ref_binary("ref_v3redo_scene0_exact"):
+        pytest.skip("ref_v3redo_scene0_exact not built")
+    W, H = 256, 144
+    env = po.synthetic_env(256, 128)
+    o, _ = oracle.render(po.PROFILE_V3REDO_SCENE0, W, H, tiles[0], tiles[1], bounces, frames, env=env, env_kind=po.ENV_EQUIRECT,
+                         env_sampler=po.SAMPLER_BILINEAR)
+    r = po.run_ref("ref_v3redo_scene0_exact", W, H, tiles[0], tiles[1], frames, bounces=bounces, env=env)["buffer"]
+    assert np.array_equal(o, r)
+    # a different picture than SCENE 1
+    o1, _ = oracle.render(po.PROFILE_V3REDO, W, H, tiles[0], tiles[1], bounces, frames, env=env, env_kind=po.ENV_EQUIRECT,
+                          env_sampler=po.SAMPLER_BILINEAR)
+    assert not np.array_equal(o, o1)
+
+
+@needs_ref
 @pytest.mark.skipif(not os.path.exists(os.path.join(TEX_DIR, "HDR_040_Field_Env.hdr")), reason="reference textures absent")
 def test_v4_real_textures(oracle, tmp_path):
     """The reference's shipped HDR env maps, decoded by the reference's own loader (stb_image)."""
