@@ -4,6 +4,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
 #include <string>
 
 #include "b200pt.h"
@@ -162,7 +163,13 @@ texture LoadTexture(char* filename)
     texture t;
     b200pt::HostImage img;
     std::string err;
-    if (!b200pt::LoadRadianceHDR(filename, &img, &err)) {
+    bool ok = false;
+    try {
+        ok = b200pt::LoadRadianceHDR(filename, &img, &err);
+    } catch (const std::exception& e) {
+        err = e.what();
+    }
+    if (!ok) {
         std::fprintf(stderr, "LoadTexture(%s): %s\n", filename, err.c_str());
         return t;  // Data == 0, like a failed stbi_loadf
     }
@@ -180,7 +187,13 @@ texture LoadCubemapTexture(char* filename[6])
     b200pt::HostImage img;
     std::string err, paths[6];
     for (int i = 0; i < 6; i++) paths[i] = filename[i];
-    if (!b200pt::LoadCubemapAtlas(paths, &img, &err)) {
+    bool ok = false;
+    try {
+        ok = b200pt::LoadCubemapAtlas(paths, &img, &err);
+    } catch (const std::exception& e) {
+        err = e.what();
+    }
+    if (!ok) {
         std::fprintf(stderr, "LoadCubemapTexture: %s\n", err.c_str());
         return t;
     }

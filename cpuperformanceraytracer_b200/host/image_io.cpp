@@ -33,7 +33,13 @@ bool read_file(const std::string& path, std::vector<uint8_t>* out, std::string* 
 struct Cursor {
     const uint8_t* p;
     const uint8_t* end;
-    int get() { return p < end ? *p++ : 0; }  // reads past the end yield zeros, like stb's get8
+    bool overrun = false;
+    int get()
+    {
+        if (p < end) return *p++;
+        overrun = true;  // the decoder fails on truncated pixel data instead of zero-filling it
+        return 0;
+    }
     bool eof() const { return p >= end; }
     std::string line()
     {
@@ -68,7 +74,7 @@ bool DecodeRadianceHDR(const uint8_t* data, size_t size, HostImage* out, std::st
         if (err) *err = m;
         return false;
     };
-    Cursor c{data, data + size};
+    Cursor c{data, data + size, false};
     const std::string magic = c.line();
     if (magic != "#?RADIANCE" && magic != "#?RGBE") return fail("not a Radiance HDR file");
     bool rle_rgbe = false;
@@ -84,13 +90,20 @@ bool DecodeRadianceHDR(const uint8_t* data, size_t size, HostImage* out, std::st
     if (std::sscanf(dims.c_str(), "-Y %d +X %d", &h, &w) != 2 || w <= 0 || h <= 0 || w > (1 << 24) || h > (1 << 24))
         return fail("unsupported HDR data layout (need -Y h +X w)");
 
-    std::vector<float> top_down((size_t)w * h * 3);
-    std::vector<uint8_t> scan((size_t)w * 4);
     bool flat = (w < 8 || w >= 32768);
     if (!flat) {
         // new-style RLE scanlines start with 2, 2, hi, lo (hi < 128); anything else means flat data
         if (c.end - c.p >= 4 && !(c.p[0] == 2 && c.p[1] == 2 && !(c.p[2] & 0x80))) flat = true;
     }
+    // Size the image against the bytes that are actually there BEFORE allocating: a flat file holds 4 bytes per pixel, an
+    // RLE one at least 4 marker bytes + 2 bytes per channel per scanline.  The renderer cannot use more than 2^24 floats
+    // either (the reference indexes texels through binary32 arithmetic, texture.cpp:56-65; b200pt_set_env enforces it).
+    const size_t remaining = (size_t)(c.end - c.p);
+    const unsigned long long pixels = (unsigned long long)w * (unsigned long long)h;
+    if (pixels * 3ull >= (1ull << 24)) return fail("HDR image too large (>= 2^24 floats)");
+    if (flat ? pixels * 4ull > remaining : (unsigned long long)h * 12ull > remaining) return fail("truncated HDR pixel data");
+    std::vector<float> top_down((size_t)w * h * 3);
+    std::vector<uint8_t> scan((size_t)w * 4);
     if (flat) {
         for (size_t i = 0; i < (size_t)w * h; i++) {
             uint8_t px[4] = {(uint8_t)c.get(), (uint8_t)c.get(), (uint8_t)c.get(), (uint8_t)c.get()};
@@ -117,9 +130,11 @@ bool DecodeRadianceHDR(const uint8_t* data, size_t size, HostImage* out, std::st
                     }
                 }
             }
+            if (c.overrun) return fail("truncated HDR pixel data");
             for (int i = 0; i < w; i++) rgbe_to_float(&scan[(size_t)i * 4], &top_down[((size_t)j * w + i) * 3]);
         }
     }
+    if (c.overrun) return fail("truncated HDR pixel data");
     // stbi_set_flip_vertically_on_load(true), asset_loading.cpp:12
     out->width = w;
     out->height = h;
@@ -223,17 +238,25 @@ int b200pt_io_load_hdr(const char* path, float** data, int* width, int* height)
 {
     b200pt::HostImage img;
     std::string err;
-    if (!path || !data || !width || !height || !b200pt::LoadRadianceHDR(path, &img, &err)) return 1;
-    return export_image(img, data, width, height);
+    try {  // no exception may cross the C boundary (std::bad_alloc on a hostile header, ...)
+        if (!path || !data || !width || !height || !b200pt::LoadRadianceHDR(path, &img, &err)) return 1;
+        return export_image(img, data, width, height);
+    } catch (...) {
+        return 1;
+    }
 }
 int b200pt_io_load_cubemap(const char* const paths[6], float** data, int* width, int* height)
 {
     b200pt::HostImage img;
     std::string err, p[6];
     if (!paths || !data || !width || !height) return 1;
-    for (int i = 0; i < 6; i++) p[i] = paths[i] ? paths[i] : "";
-    if (!b200pt::LoadCubemapAtlas(p, &img, &err)) return 1;
-    return export_image(img, data, width, height);
+    try {
+        for (int i = 0; i < 6; i++) p[i] = paths[i] ? paths[i] : "";
+        if (!b200pt::LoadCubemapAtlas(p, &img, &err)) return 1;
+        return export_image(img, data, width, height);
+    } catch (...) {
+        return 1;
+    }
 }
 int b200pt_io_write_bmp32(const char* path, int width, int height, const uint32_t* rgba)
 {

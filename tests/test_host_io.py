@@ -121,6 +121,21 @@ def test_hdr_reader_rejects_garbage(io, tmp_path):
     p.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_xyze\n\n-Y 1 +X 1\n\0\0\0\0")
     assert load_hdr(io, p) is None
     assert load_hdr(io, tmp_path / "missing.hdr") is None
+    # a hostile header: 16M x 16M pixels with 4 bytes of data -> rejected before any allocation
+    p.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 16777216 +X 16777216\n\0\0\0\0")
+    assert load_hdr(io, p) is None
+    # larger than the renderer's 2^24-float texel indexing
+    p.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 4096 +X 4096\n" + b"\0" * 64)
+    assert load_hdr(io, p) is None
+    # truncated pixel data: flat (fewer than 4 bytes per pixel) and RLE (a scanline cut short) fail instead of zero-filling
+    p.write_bytes(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n-Y 2 +X 4\n" + b"\x10\x20\x30\x80" * 7)
+    assert load_hdr(io, p) is None
+    good = tmp_path / "good.hdr"
+    write_hdr(good, rgbe_encode(np.full((4, 16, 3), 0.5, dtype=np.float32)), rle=True)
+    b = good.read_bytes()
+    assert load_hdr(io, good) is not None
+    p.write_bytes(b[:-9])
+    assert load_hdr(io, p) is None
 
 
 def test_bmp_writer_layout(io, tmp_path):
