@@ -28,7 +28,7 @@ ABI_SYMBOLS = [
     "b200pt_get_frame_counter", "b200pt_render_frames", "b200pt_synchronize", "b200pt_upload_target",
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
-    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_set_tile_stride", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_present_blocking", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4",
+    "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_set_tile_stride", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_present_blocking", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4", "b200pt_set_scene_cornell", "b200pt_compute_cull_rects_scene_cornell",
     "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_scale_target", "b200pt_scale_target_span",
     "b200pt_group_create", "b200pt_group_destroy", "b200pt_group_size", "b200pt_group_context", "b200pt_group_set_env",
     "b200pt_group_resize", "b200pt_group_reset", "b200pt_group_set_bands", "b200pt_group_set_frame_counter", "b200pt_group_get_frame_counter",
@@ -103,6 +103,8 @@ def load_library():
     L.b200pt_set_tile_range.argtypes = [vp, i32, i32]
     L.b200pt_set_tile_stride.argtypes = [vp, i32, i32]
     L.b200pt_set_scene_v4.argtypes = [vp, vp, i32, vp, i32, vp, vp]
+    L.b200pt_set_scene_cornell.argtypes = [vp, vp, vp, vp]
+    L.b200pt_compute_cull_rects_scene_cornell.argtypes = [vp, vp, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     L.b200pt_present_submit.argtypes = [vp, i32]
     L.b200pt_present_acquire.argtypes = [vp, ctypes.POINTER(ctypes.POINTER(ctypes.c_uint32)), ctypes.POINTER(i32)]
     L.b200pt_present_blocking.argtypes = [vp, i32, ctypes.POINTER(ctypes.c_uint32), i32]
@@ -227,6 +229,19 @@ class Renderer:
         rc = self._lib.b200pt_set_scene_v4(self._ctx, q.ctypes.data_as(ctypes.c_void_p), q.shape[0], s.ctypes.data_as(ctypes.c_void_p),
                                            s.shape[0], m.ctypes.data_as(ctypes.c_void_p), cam.ctypes.data_as(ctypes.c_void_p))
         self._check(rc, "b200pt_set_scene_v4")
+
+    def set_scene_cornell(self, quads=None, spheres=None, materials=None):
+        """Cornell-family profiles: quads (6, 4, 3) vertices, spheres (3, 4) xyz + radius, materials (9, 11) in
+        b200pt_material_legacy order.  No arguments: back to the reference's box."""
+        if quads is None:
+            self._check(self._lib.b200pt_set_scene_cornell(self._ctx, None, None, None), "b200pt_set_scene_cornell")
+            return
+        q = np.ascontiguousarray(quads, dtype=np.float32).reshape(6, 12)
+        s = np.ascontiguousarray(spheres, dtype=np.float32).reshape(3, 4)
+        m = np.ascontiguousarray(materials, dtype=np.float32).reshape(9, 11)
+        vp = ctypes.c_void_p
+        rc = self._lib.b200pt_set_scene_cornell(self._ctx, q.ctypes.data_as(vp), s.ctypes.data_as(vp), m.ctypes.data_as(vp))
+        self._check(rc, "b200pt_set_scene_cornell")
 
     def resize(self, width, height, ntx, nty):
         self._check(self._lib.b200pt_resize(self._ctx, width, height, ntx, nty), "b200pt_resize")
@@ -517,6 +532,20 @@ def cull_rects_scene_v4(quads, spheres, camera_position, camera_distance, width,
                                               cam.ctypes.data_as(vp), width, height, r, ctypes.byref(n))
     if rc != 0:
         raise B200PTError("b200pt_compute_cull_rects_scene_v4: invalid argument")
+    return None if n.value < 0 else np.array(r[:4 * n.value], dtype=np.float32).reshape(n.value, 4)
+
+
+def cull_rects_scene_cornell(quads, spheres, width, height):
+    """Host-only: culling rectangles of a run-time Cornell-family scene, or None when culling is impossible."""
+    L = load_library()
+    q = np.ascontiguousarray(quads, dtype=np.float32).reshape(6, 12)
+    s = np.ascontiguousarray(spheres, dtype=np.float32).reshape(3, 4)
+    r = (ctypes.c_float * 48)()
+    n = ctypes.c_int32()
+    vp = ctypes.c_void_p
+    rc = L.b200pt_compute_cull_rects_scene_cornell(q.ctypes.data_as(vp), s.ctypes.data_as(vp), width, height, r, ctypes.byref(n))
+    if rc != 0:
+        raise B200PTError("b200pt_compute_cull_rects_scene_cornell: invalid argument")
     return None if n.value < 0 else np.array(r[:4 * n.value], dtype=np.float32).reshape(n.value, 4)
 
 

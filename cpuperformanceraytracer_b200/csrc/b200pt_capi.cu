@@ -380,6 +380,45 @@ int b200pt_set_scene_v4(b200pt_context* c, const b200pt_quad* quads, int32_t num
     return B200PT_OK;
 }
 
+int b200pt_set_scene_cornell(b200pt_context* c, const b200pt_quad* quads, const b200pt_sphere* spheres, const b200pt_material_legacy* materials)
+{
+    if (!c) return B200PT_ERR_INVALID_ARGUMENT;
+    if (c->params.profile != B200PT_PROFILE_V2 && c->params.profile != B200PT_PROFILE_SIMT_TEXTURED)
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "b200pt_set_scene_cornell is for the V2 / SIMT_TEXTURED profiles");
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
+    CUDA_TRY(c, cudaStreamSynchronize(c->stream));
+    if (!quads) {  // back to the literals of v2.cpp:320-454
+        build_cornell_scene(&c->scenes.cornell, c->params.profile == B200PT_PROFILE_SIMT_TEXTURED);
+        c->custom_scene = false;
+        return B200PT_OK;
+    }
+    if (!spheres || !materials) return fail(c, B200PT_ERR_INVALID_ARGUMENT, "6 quads, 3 spheres and 9 materials are required");
+    static_assert(sizeof(b200pt_material_legacy) == 11 * sizeof(float), "plain float record");
+    CornellScene s;
+    if (!build_cornell_scene_from(&s, reinterpret_cast<const float*>(quads), reinterpret_cast<const float*>(spheres),
+                                  reinterpret_cast<const float*>(materials)))
+        return fail(c, B200PT_ERR_INVALID_ARGUMENT, "coordinates must lie within +-1e6, radii in [1e-3, 1e6]");
+    c->scenes.cornell = s;
+    c->custom_scene = true;
+    c->scene_quads.assign(reinterpret_cast<const float*>(quads), reinterpret_cast<const float*>(quads) + 12 * kCornellQuads);
+    c->scene_spheres.assign(reinterpret_cast<const float*>(spheres), reinterpret_cast<const float*>(spheres) + 4 * kCornellSpheres);
+    return B200PT_OK;
+}
+
+int b200pt_compute_cull_rects_scene_cornell(const b200pt_quad* quads, const b200pt_sphere* spheres, int32_t width, int32_t height,
+                                            float* rects, int32_t* count)
+{
+    if (!quads || !spheres || !rects || !count || width <= 0 || height <= 0) return B200PT_ERR_INVALID_ARGUMENT;
+    float4 r[kMaxCullRects];
+    const int n = compute_cull_rects_cornell(reinterpret_cast<const float*>(quads), reinterpret_cast<const float*>(spheres), width, height, r);
+    *count = n;
+    for (int i = 0; i < n; i++) {
+        rects[4 * i + 0] = r[i].x; rects[4 * i + 1] = r[i].y; rects[4 * i + 2] = r[i].z; rects[4 * i + 3] = r[i].w;
+    }
+    return B200PT_OK;
+}
+
 int b200pt_resize(b200pt_context* c, int32_t width, int32_t height, int32_t ntx, int32_t nty)
 {
     if (!c) return B200PT_ERR_INVALID_ARGUMENT;
@@ -524,6 +563,8 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
         rp.res_div_exact = (sig_bits((unsigned)c->width) <= 16 && sig_bits((unsigned)c->height) <= 16) ? 1 : 0;
     }
     if (c->params.disable_camera_culling) rp.num_cull_rects = -1;
+    else if (c->custom_scene && c->params.profile != B200PT_PROFILE_OPT_V4)
+        rp.num_cull_rects = compute_cull_rects_cornell(c->scene_quads.data(), c->scene_spheres.data(), c->width, c->height, rp.cull_rect);
     else if (c->custom_scene)
         rp.num_cull_rects = compute_cull_rects_v4(c->scene_quads.data(), c->scenes.v4.numQuads, c->scene_spheres.data(),
                                                   c->scenes.v4.numSpheres, c->scene_cam, c->scene_cam[3], c->width, c->height, rp.cull_rect);

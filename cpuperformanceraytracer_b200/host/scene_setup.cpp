@@ -73,6 +73,38 @@ void build_cornell_scene(CornellScene* s, bool simt_textured_materials)
     }
 }
 
+bool build_cornell_scene_from(CornellScene* s, const float* qv, const float* sp, const float* mats)
+{
+    std::memset(s, 0, sizeof(*s));
+    for (int i = 0; i < kCornellQuads * 12; i++)
+        if (!(std::fabs(qv[i]) <= 1e6f)) return false;
+    for (int i = 0; i < kCornellSpheres; i++) {
+        for (int k = 0; k < 3; k++)
+            if (!(std::fabs(sp[4 * i + k]) <= 1e6f)) return false;
+        if (!(sp[4 * i + 3] >= 1e-3f && sp[4 * i + 3] <= 1e6f)) return false;
+    }
+    for (int i = 0; i < kCornellQuads; i++) {
+        LegacyQuad& q = s->quad[i];
+        const float* v = qv + 12 * i;
+        q.a = mk(v[0], v[1], v[2]);
+        q.b = mk(v[3], v[4], v[5]);
+        q.c = mk(v[6], v[7], v[8]);
+        q.d = mk(v[9], v[10], v[11]);
+        q.n = normalize(cross(sub(q.c, q.a), sub(q.c, q.b)));  // v2.cpp:166
+    }
+    for (int i = 0; i < kCornellSpheres; i++) s->sphere[i] = make_float4(sp[4 * i], sp[4 * i + 1], sp[4 * i + 2], sp[4 * i + 3]);
+    for (int i = 0; i < kCornellObjects; i++) {
+        const float* m = mats + 11 * i;
+        LegacyMaterial& d = s->mat[i];
+        d.albedo = mk(m[0], m[1], m[2]);
+        d.emissive = mk(m[3], m[4], m[5]);
+        d.specularColor = mk(m[6], m[7], m[8]);
+        d.percentSpecular = m[9];
+        d.roughness = m[10];
+    }
+    return true;
+}
+
 // PrecomputeQuadData, v4.cpp:269-319
 static void precompute_quad(V4Quad* q, v3 V0, v3 V1, v3 V2, v3 V3)
 {
@@ -304,6 +336,27 @@ int compute_cull_rects_v4(const float* qv, int nq, const float* sp, int ns, cons
     for (int i = 0; i < ns; i++)
         if (!project_box(sphere_box(make_float4(sp[4 * i], sp[4 * i + 1], sp[4 * i + 2], std::fabs(sp[4 * i + 3]))), kProfileV4, width,
                          height, cam_dist, &rects[n++], cp))
+            return -1;
+    return n;
+}
+
+int compute_cull_rects_cornell(const float* qv, const float* sp, int width, int height, float4* rects)
+{
+    const double camDist = camera_distance();
+    int n = 0;
+    for (int i = 0; i < kCornellQuads; i++) {
+        Box b = empty_box();
+        for (int k = 0; k < 4; k++) grow(&b, mk(qv[12 * i + 3 * k], qv[12 * i + 3 * k + 1], qv[12 * i + 3 * k + 2]));
+        for (int a = 0; a < 3; a++) {
+            const double pad = 1e-3 + 1e-5 * (std::fabs(b.lo[a]) + std::fabs(b.hi[a]));
+            b.lo[a] -= pad;
+            b.hi[a] += pad;
+        }
+        if (!project_box(b, kProfileV2, width, height, camDist, &rects[n++])) return -1;
+    }
+    for (int i = 0; i < kCornellSpheres; i++)
+        if (!project_box(sphere_box(make_float4(sp[4 * i], sp[4 * i + 1], sp[4 * i + 2], std::fabs(sp[4 * i + 3]))), kProfileV2, width, height,
+                         camDist, &rects[n++]))
             return -1;
     return n;
 }

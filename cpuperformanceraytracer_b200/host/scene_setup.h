@@ -13,6 +13,13 @@ void build_v3redo_scene0(V3RedoScene0* s);
 // SceneMaterial (v4.cpp:351-362); like AddMaterialToScene, albedo.y / albedo.z are replaced by albedo.x.
 bool build_v4_scene_from(V4Scene* s, const float* quad_vertices, int num_quads, const float* spheres, int num_spheres,
                          const float* materials, const float camera_position[3], float camera_distance);
+// The Cornell-family scene (v2.cpp:320-454: six quads, three spheres, nine materials) from caller data: quads as 4
+// vertices (12 floats each, already translated), spheres as xyz + radius, materials as 11 floats in LegacyMaterial order
+// (albedo3, emissive3, specularColor3, percentSpecular, roughness).  The quad normals are the reference's per-ray
+// expression normalize(cross(c - a, c - b)) (v2.cpp:166) evaluated once.  false: a coordinate outside +-1e6 / a radius
+// outside [1e-3, 1e6] (the kernels' unchecked reciprocal / division sequences are proven for scene-scale operands only).
+bool build_cornell_scene_from(CornellScene* s, const float* quad_vertices, const float* spheres, const float* materials);
+int compute_cull_rects_cornell(const float* quad_vertices, const float* spheres, int width, int height, float4* rects);
 // culling rectangles for an arbitrary v4-profile scene (quad vertices / spheres as above)
 int compute_cull_rects_v4(const float* quad_vertices, int num_quads, const float* spheres, int num_spheres,
                           const float camera_position[3], float camera_distance, int width, int height, float4* rects);

@@ -150,6 +150,11 @@ typedef struct b200pt_material {                                                
     float refractionColor[3];
 } b200pt_material;
 typedef struct b200pt_camera { float Position[3]; float Distance; } b200pt_camera;       /* Camera, :380-386 */
+/* SMaterialInfo of the Cornell-family renderers (demofox_path_tracing_v2.cpp:39-50; simt_textured uses albedo / emissive) */
+typedef struct b200pt_material_legacy {
+    float albedo[3], emissive[3], specularColor[3];
+    float percentSpecular, roughness;
+} b200pt_material_legacy;
 int b200pt_set_scene_v4(b200pt_context* ctx, const b200pt_quad* quads, int32_t num_quads, const b200pt_sphere* spheres,
                         int32_t num_spheres, const b200pt_material* materials, const b200pt_camera* camera);
 
@@ -303,6 +308,19 @@ int b200pt_group_resolve_ldr(b200pt_group* group, uint32_t* host_dst, int32_t mo
  * copies): the part of the exchange that is NOT hidden behind rendering (it includes waiting for slower ranks) */
 int b200pt_group_get_counters(b200pt_group* group, b200pt_counters* out, double* combine_ms);
 const char* b200pt_group_last_error(b200pt_group* group);
+
+/* The Cornell-family scene (B200PT_PROFILE_V2 / _SIMT_TEXTURED) as data.  The reference writes it as literals inside its
+ * trace function (demofox_path_tracing_v2.cpp:320-454, ..._simt_textured.cpp:278-385): exactly 6 quads (vertices A B C D,
+ * scene translation already applied), 3 spheres, 9 materials (quads first).  The primitive counts are the renderer's own
+ * (its trace is unrolled over them); positions, sizes and materials are free.  The generic kernel (vertex data read from
+ * the scene table instead of immediates) renders it, bit-exact against the oracle on random scenes.  Coordinates must lie
+ * within +-1e6, radii in [1e-3, 1e6].  quads == NULL: back to the reference's box.  Not thread-safe against in-flight
+ * renders on the same context (it synchronises the stream first). */
+int b200pt_set_scene_cornell(b200pt_context* ctx, const b200pt_quad* quads /* 6 */, const b200pt_sphere* spheres /* 3 */,
+                             const b200pt_material_legacy* materials /* 9 */);
+/* host-only: the culling rectangles such a scene gets (count < 0: culling impossible) */
+int b200pt_compute_cull_rects_scene_cornell(const b200pt_quad* quads, const b200pt_sphere* spheres, int32_t width, int32_t height,
+                                            float* rects, int32_t* count);
 
 /* debug/parity hook: u32 RNG state of every pixel after the last rendered frame's path ended
  * (row-major W*H, row 0 = top); checks wang_hash stream parity bit for bit */

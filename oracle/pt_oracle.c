@@ -227,6 +227,25 @@ static void cornell_init(cornell_t* s, int profile)
     }
 }
 
+static void cornell_from(cornell_t* s, const oracle_scene_cornell* src)
+{
+    for (int i = 0; i < 6; i++)
+        for (int k = 0; k < 4; k++) s->quad[i][k] = V3(src->quad_vertices[12 * i + 3 * k], src->quad_vertices[12 * i + 3 * k + 1], src->quad_vertices[12 * i + 3 * k + 2]);
+    for (int i = 0; i < 3; i++) {
+        s->sphereCenter[i] = V3(src->spheres[4 * i], src->spheres[4 * i + 1], src->spheres[4 * i + 2]);
+        s->sphereRadius[i] = src->spheres[4 * i + 3];
+    }
+    memset(s->mat, 0, sizeof(s->mat));
+    for (int i = 0; i < 9; i++) {
+        const float* m = src->materials + 11 * i;
+        s->mat[i].albedo = V3(m[0], m[1], m[2]);
+        s->mat[i].emissive = V3(m[3], m[4], m[5]);
+        s->mat[i].specularColor = V3(m[6], m[7], m[8]);
+        s->mat[i].percentSpecular = m[9];
+        s->mat[i].roughness = m[10];
+    }
+}
+
 static void TestSceneTrace_cornell(const cornell_t* s, v3 rayPos, v3 rayDir, hit_t* h)
 {
     for (int i = 0; i < 6; i++)
@@ -959,6 +978,10 @@ static int ctx_init(ctx_t* c, const oracle_params* p)
     if (needs_env && (!p->env || p->env_width <= 0 || p->env_height <= 0)) return -1;
     c->p = p;
     cornell_init(&c->cornell, p->profile);
+    if (p->scene_cornell && (p->profile == ORACLE_PROFILE_V2 || p->profile == ORACLE_PROFILE_SIMT_TEXTURED)) {
+        if (!p->scene_cornell->quad_vertices || !p->scene_cornell->spheres || !p->scene_cornell->materials) return -1;
+        cornell_from(&c->cornell, p->scene_cornell);
+    }
     scene4_init(&c->scene4);
     if (p->profile == ORACLE_PROFILE_V4 && p->scene_v4 && scene4_from(&c->scene4, p->scene_v4)) return -1;
     scene3_init(&c->scene3, p->profile == ORACLE_PROFILE_V3REDO_SCENE0 ? 0 : 1);

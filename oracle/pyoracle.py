@@ -26,6 +26,11 @@ class OracleSceneV4(ctypes.Structure):
                 ("camera_position", ctypes.c_float * 3), ("camera_distance", ctypes.c_float)]
 
 
+class OracleSceneCornell(ctypes.Structure):
+    _fields_ = [("quad_vertices", ctypes.POINTER(ctypes.c_float)), ("spheres", ctypes.POINTER(ctypes.c_float)),
+                ("materials", ctypes.POINTER(ctypes.c_float))]
+
+
 class OracleParams(ctypes.Structure):
     _fields_ = [
         ("profile", ctypes.c_int),
@@ -40,6 +45,7 @@ class OracleParams(ctypes.Structure):
         ("env_width", ctypes.c_int),
         ("env_height", ctypes.c_int),
         ("scene_v4", ctypes.POINTER(OracleSceneV4)),
+        ("scene_cornell", ctypes.POINTER(OracleSceneCornell)),
     ]
 
 
@@ -96,6 +102,16 @@ def make_scene_v4(quads, spheres, materials, camera_position=(0.0, 0.0, 40.0), c
     return sc, (q, s, m)
 
 
+def make_scene_cornell(quads, spheres, materials):
+    """(6, 4, 3) vertices, (3, 4) xyz + radius, (9, 11) legacy materials -> (OracleSceneCornell, keep-alive arrays)"""
+    q = np.ascontiguousarray(quads, dtype=np.float32).reshape(6, 12)
+    s = np.ascontiguousarray(spheres, dtype=np.float32).reshape(3, 4)
+    m = np.ascontiguousarray(materials, dtype=np.float32).reshape(9, 11)
+    fp = ctypes.POINTER(ctypes.c_float)
+    sc = OracleSceneCornell(q.ctypes.data_as(fp), s.ctypes.data_as(fp), m.ctypes.data_as(fp))
+    return sc, (q, s, m)
+
+
 def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=ENV_NONE, env_sampler=SAMPLER_POINT):
     p = OracleParams()
     p.profile, p.width, p.height = profile, width, height
@@ -111,11 +127,14 @@ def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=EN
 
 
 def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, env=None, env_kind=ENV_NONE,
-           env_sampler=SAMPLER_POINT, target=None, nthreads=0, scene_v4=None):
-    """Returns (tile-major f32 buffer, counters dict).  scene_v4: result of make_scene_v4 (V4 profile)."""
+           env_sampler=SAMPLER_POINT, target=None, nthreads=0, scene_v4=None, scene_cornell=None):
+    """Returns (tile-major f32 buffer, counters dict).  scene_v4: result of make_scene_v4 (V4 profile);
+    scene_cornell: result of make_scene_cornell (V2 / SIMT_TEXTURED profiles)."""
     p, keep = make_params(profile, width, height, ntx, nty, bounces, env, env_kind, env_sampler)
     if scene_v4 is not None:
         p.scene_v4 = ctypes.pointer(scene_v4[0])
+    if scene_cornell is not None:
+        p.scene_cornell = ctypes.pointer(scene_cornell[0])
     if target is None:
         target = np.zeros(width * height * 3, dtype=np.float32)
     else:
@@ -130,11 +149,13 @@ def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, en
 
 
 def max_segments(profile, width, height, bounces, nframes, first_frame=1, env=None, env_kind=ENV_NONE,
-                 env_sampler=SAMPLER_POINT, scene_v4=None):
+                 env_sampler=SAMPLER_POINT, scene_v4=None, scene_cornell=None):
     """(H, W) uint32: max traced segments per pixel over the frame range."""
     p, keep = make_params(profile, width, height, 1, 1, bounces, env, env_kind, env_sampler)
     if scene_v4 is not None:
         p.scene_v4 = ctypes.pointer(scene_v4[0])
+    if scene_cornell is not None:
+        p.scene_cornell = ctypes.pointer(scene_cornell[0])
     out = np.zeros(width * height, dtype=np.uint32)
     L = lib()
     L.oracle_max_segments.argtypes = [ctypes.POINTER(OracleParams), ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_uint32)]
