@@ -36,7 +36,7 @@ ABI_SYMBOLS = [
     "b200pt_group_render_host", "b200pt_group_resolve_ldr", "b200pt_group_get_counters", "b200pt_group_last_error",
 ]
 SHARD_SPP, SHARD_TILES = 0, 1
-COMBINE_NCCL, COMBINE_PEER = 0, 1
+COMBINE_NCCL, COMBINE_PEER, COMBINE_FUSED = 0, 1, 2
 FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP, FN_SQRT, FN_RCP, FN_DIV, FN_EQUIRECT_TEXEL = 0, 1, 2, 3, 4, 5, 6, 7, 8
 
 

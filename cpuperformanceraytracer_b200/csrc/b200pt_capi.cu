@@ -570,6 +570,10 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
                                                   c->scenes.v4.numSpheres, c->scene_cam, c->scene_cam[3], c->width, c->height, rp.cull_rect);
     else rp.num_cull_rects = compute_cull_rects(c->params.profile, c->width, c->height, rp.cull_rect);
 
+    if (c->scatter_gpo > 0 && c->params.accum_mode == B200PT_ACCUM_SUM && c->num_tiles == 0 && c->tile_mod <= 1) {
+        rp.scatter_gpo = c->scatter_gpo;
+        for (int i = 0; i < kMaxScatterRanks; i++) rp.scatter_stage[i] = c->scatter_stage[i];
+    }
     {
         const int rc = ensure_item_order(c, rp);
         if (rc != B200PT_OK) return rc;

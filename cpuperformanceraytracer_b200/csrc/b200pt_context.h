@@ -64,6 +64,9 @@ struct b200pt_context {
 
     int iframe = 0;
     int first_tile = 0, num_tiles = 0;  // flat tile range rendered by this context (0, 0 = all tiles)
+    // set by b200pt_group (B200PT_COMBINE_FUSED) around a launch: see RenderParams::scatter_stage
+    float* scatter_stage[kMaxScatterRanks] = {};
+    int scatter_gpo = 0;
     int tile_mod = 0, tile_rem = 0;     // or: every tile_mod-th tile (FlatTileIndex % tile_mod == tile_rem); 0 = off
     int blocks_per_sm = 0;
     bool sorted = false;           // B200PT_SCHED_SORTED: pt_render_sorted_kernel instead of pt_render_kernel

@@ -112,6 +112,49 @@ __global__ void __launch_bounds__(256) peer_combine_kernel(const __grid_constant
     }
 }
 
+// ---- K6: the owner's half of the FUSED render + reduce-scatter (B200PT_COMBINE_FUSED) ------------------------------------
+// The render kernels of all ranks have already stored their partial sums of THIS rank's part of the image into this rank's
+// staging buffer, slot q for rank q (RenderParams::scatter_stage: remote stores over NVLink issued pixel by pixel while the
+// render runs, so the exchange is spread over the whole launch instead of following it).  What is left is local: add the
+// nsrc slots in rank order, add rank 0's previous image times (F + 1) (the sum it stands for), scale by 1/(iFrame + 1), and
+// store the finished slice into rank 0's buffer.  16 nsrc B of local HBM reads + one 16 B remote read and write per float4.
+struct StagedCombineParams {
+    const float4* stage;  // this rank's staging buffer: nslots slots of `slot4` float4
+    float4* image;        // rank 0's target + this rank's slice
+    size_t slot4, count4;
+    int nsrc;
+    float prev_factor, scale;
+};
+
+__global__ void __launch_bounds__(256) staged_combine_kernel(const __grid_constant__ StagedCombineParams p)
+{
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < p.count4; i += stride) {
+        const float4 prev = p.image[i];
+        float4 a = __ldg(p.stage + i);
+        for (int q = 1; q < p.nsrc; q++) {
+            const float4 v = __ldg(p.stage + (size_t)q * p.slot4 + i);
+            a.x += v.x;
+            a.y += v.y;
+            a.z += v.z;
+            a.w += v.w;
+        }
+        a.x = (a.x + prev.x * p.prev_factor) * p.scale;
+        a.y = (a.y + prev.y * p.prev_factor) * p.scale;
+        a.z = (a.z + prev.z * p.prev_factor) * p.scale;
+        a.w = (a.w + prev.w * p.prev_factor) * p.scale;
+        p.image[i] = a;
+    }
+}
+
+cudaError_t launch_staged_combine(const StagedCombineParams& p, int sm_count, cudaStream_t stream)
+{
+    if (p.count4 == 0) return cudaSuccess;
+    const size_t want = (p.count4 + 255) / 256, cap = (size_t)sm_count * 8;
+    staged_combine_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_peer_combine(const PeerCombineParams& p, int sm_count, cudaStream_t stream)
 {
     if (p.count == 0) return cudaSuccess;
@@ -146,6 +189,9 @@ struct b200pt_group {
     double combine_ms = 0.0;
     int width = 0, height = 0, ntx = 0, nty = 0;
     int tile_first[kMaxGroup] = {}, tile_count[kMaxGroup] = {};  // B200PT_SHARD_TILES: flat tile ranges ...
+    float* stage[kMaxGroup] = {};   // B200PT_COMBINE_FUSED: per rank, n slots of one slice each
+    size_t stage_floats = 0;        // size of every stage
+    int stage_gpo = 0;              // SoA8 groups per owner
     bool tile_stride = false;  // ... or rank r renders the tiles with FlatTileIndex % n == r (interleaved: balanced by construction)
     bool peer_all = true;      // every rank can address rank 0's memory
     int iframe = 0;
@@ -249,10 +295,82 @@ int auto_bands(const b200pt_group* g)
     return g->bands < g->nty ? g->bands : g->nty;
 }
 
+// B200PT_COMBINE_FUSED: the render kernels scatter their partial sums to the owners' stages while they run (K1 epilogue),
+// the owners finish locally (K6).  Rank 0's buffer keeps the image (running average) between calls; the other ranks'
+// targets are not used at all.
+int render_spp_fused(b200pt_group* g, int nframes)
+{
+    const int F = g->iframe, n = g->n;
+    const size_t slice = (size_t)g->stage_gpo * 24, nfl = image_floats(g);
+    int active = 0;
+    for (int r = 0; r < n; r++) {
+        size_t first, count;
+        block_of((size_t)nframes, n, r, &first, &count);
+        b200pt_context* c = g->ctx[r];
+        c->scatter_gpo = g->stage_gpo;
+        for (int o = 0; o < n; o++) c->scatter_stage[o] = g->stage[o] + (size_t)r * slice;  // owner o's stage, slot r
+        c->iframe = F + (int)first;
+        int rc = B200PT_OK;
+        if (count > 0) {
+            rc = b200pt_render_frames(c, (int32_t)count);
+            active = r + 1;  // block_of hands the frames to the first ranks: the active ones are 0 .. active-1
+        }
+        c->scatter_gpo = 0;
+        c->iframe = F + nframes;
+        if (rc != B200PT_OK) return cfail(g, r, rc, "b200pt_render_frames");
+        rc = record(g, r, g->render_done[r]);
+        if (rc != B200PT_OK) return rc;
+    }
+    {
+        DeviceGuard guard(g->device[0]);
+        GROUP_CUDA(g, guard.status);
+        GROUP_CUDA(g, cudaEventRecord(g->cb0, g->ctx[0]->stream));
+    }
+    for (int r = 0; r < n; r++)
+        for (int q = 0; q < n; q++)
+            if (q != r) {
+                const int rc = stream_wait(g, r, g->render_done[q]);
+                if (rc != B200PT_OK) return rc;
+            }
+    for (int r = 0; r < n; r++) {
+        const size_t begin = (size_t)r * slice;
+        if (begin >= nfl) continue;
+        StagedCombineParams sc{};
+        sc.stage = reinterpret_cast<const float4*>(g->stage[r]);
+        sc.image = reinterpret_cast<float4*>(g->ctx[0]->d_target + begin);
+        sc.slot4 = slice / 4;
+        sc.count4 = ((begin + slice <= nfl) ? slice : nfl - begin) / 4;
+        sc.nsrc = active;
+        sc.prev_factor = (float)F + 1.f;  // rank 0 holds A_F = (A_0 + sum of F samples) / (F + 1)
+        sc.scale = 1.0f / ((float)(F + nframes) + 1.f);
+        DeviceGuard guard(g->device[r]);
+        GROUP_CUDA(g, guard.status);
+        GROUP_CUDA(g, launch_staged_combine(sc, g->ctx[r]->sm_count, g->ctx[r]->stream));
+        g->launches++;
+        GROUP_CUDA(g, cudaEventRecord(g->combine_done[r], g->ctx[r]->stream));
+    }
+    // the next call's render kernels store into these stages again: every rank waits for every owner's combine
+    for (int r = 0; r < n; r++)
+        for (int q = 0; q < n; q++)
+            if (q != r) {
+                const int rc = stream_wait(g, r, g->combine_done[q]);
+                if (rc != B200PT_OK) return rc;
+            }
+    {
+        DeviceGuard guard(g->device[0]);
+        GROUP_CUDA(g, guard.status);
+        GROUP_CUDA(g, cudaEventRecord(g->cb1, g->ctx[0]->stream));
+        g->combine_timing_pending = true;
+    }
+    g->iframe = F + nframes;
+    return B200PT_OK;
+}
+
 int render_spp(b200pt_group* g, int nframes)
 {
     const int F = g->iframe, n = g->n;
     const size_t nfl = image_floats(g);
+    if (g->combine == B200PT_COMBINE_FUSED && n > 1) return render_spp_fused(g, nframes);
     const int bands = n > 1 ? auto_bands(g) : 1;
     const size_t per_tile_row = (size_t)g->width * (size_t)(g->height / g->nty) * 3;
     // rank 0 holds the running average after F calls, A_F = (A_0 + sum of the F samples) / (F + 1) (the reference's
@@ -426,7 +544,8 @@ int b200pt_group_create(const b200pt_params* params, const int32_t* devices, int
     if (!params || !devices || !out_group || num_devices < 1 || num_devices > kMaxGroup) return B200PT_ERR_INVALID_ARGUMENT;
     *out_group = nullptr;
     if (sharding != B200PT_SHARD_SPP && sharding != B200PT_SHARD_TILES) return B200PT_ERR_INVALID_ARGUMENT;
-    if (combine != B200PT_COMBINE_NCCL && combine != B200PT_COMBINE_PEER) return B200PT_ERR_INVALID_ARGUMENT;
+    if (combine != B200PT_COMBINE_NCCL && combine != B200PT_COMBINE_PEER && combine != B200PT_COMBINE_FUSED) return B200PT_ERR_INVALID_ARGUMENT;
+    if (combine == B200PT_COMBINE_FUSED && num_devices > kMaxScatterRanks) return B200PT_ERR_INVALID_ARGUMENT;
     b200pt_group* g = new (std::nothrow) b200pt_group();
     if (!g) return B200PT_ERR_OUT_OF_MEMORY;
     g->n = num_devices;
@@ -468,7 +587,7 @@ int b200pt_group_create(const b200pt_params* params, const int32_t* devices, int
                 else if (e != cudaSuccess) can = 0;
             }
             if (!can) g->peer_all = false;
-            if (!can && sharding == B200PT_SHARD_SPP && combine == B200PT_COMBINE_PEER) rc = B200PT_ERR_CUDA;
+            if (!can && sharding == B200PT_SHARD_SPP && (combine == B200PT_COMBINE_PEER || combine == B200PT_COMBINE_FUSED)) rc = B200PT_ERR_CUDA;
         }
     }
     if (rc == B200PT_OK) {
@@ -521,8 +640,13 @@ int b200pt_group_destroy(b200pt_group* g)
         if (g->cb1) cudaEventDestroy(g->cb1);
         if (g->h_pinned) cudaFreeHost(g->h_pinned);
     }
-    for (int r = 0; r < g->n; r++)
+    for (int r = 0; r < g->n; r++) {
+        if (g->stage[r]) {
+            DeviceGuard guard(g->device[r]);
+            cudaFree(g->stage[r]);
+        }
         if (g->ctx[r]) b200pt_destroy(g->ctx[r]);
+    }
     delete g;
     return B200PT_OK;
 }
@@ -549,6 +673,26 @@ int b200pt_group_resize(b200pt_group* g, int32_t width, int32_t height, int32_t 
     g->ntx = ntx;
     g->nty = nty;
     g->iframe = 0;
+    if (g->sharding == B200PT_SHARD_SPP && g->combine == B200PT_COMBINE_FUSED && g->n > 1) {
+        const long long groups = (long long)width * height / 8;
+        g->stage_gpo = (int)((groups + g->n - 1) / g->n);
+        const size_t need = (size_t)g->stage_gpo * 24 * (size_t)g->n;
+        if (need != g->stage_floats) {
+            for (int r = 0; r < g->n; r++) {
+                DeviceGuard guard(g->device[r]);
+                GROUP_CUDA(g, guard.status);
+                if (g->stage[r]) cudaFree(g->stage[r]);
+                g->stage[r] = nullptr;
+            }
+            g->stage_floats = 0;
+            for (int r = 0; r < g->n; r++) {
+                DeviceGuard guard(g->device[r]);
+                GROUP_CUDA(g, guard.status);
+                GROUP_CUDA(g, cudaMalloc(&g->stage[r], need * sizeof(float)));
+            }
+            g->stage_floats = need;
+        }
+    }
     g->tile_stride = false;
     if (g->sharding == B200PT_SHARD_TILES && g->n > 1 && (((width / ntx) / 8) * (height / nty)) % 4 == 0) {
         // Interleaved tiles: rank r renders the tiles with FlatTileIndex % n == r, in one launch (the pull-order table lists

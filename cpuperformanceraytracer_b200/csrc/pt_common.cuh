@@ -167,6 +167,7 @@ inline bool v3redo0_spheres_match_static_tables(const float4* sphere)
 }
 
 constexpr int kMaxCullRects = 12;
+constexpr int kMaxScatterRanks = 16;
 
 struct DeviceCounters {
     unsigned long long segments;
@@ -181,6 +182,11 @@ struct RenderParams {
     uint32_t* screen;     // optional: row-major u32 image, tone-mapped in the kernel tail (OUTPUT_TO_SCREEN)
     int screen_mode;      // 0 = file packing, 1 = screen packing
     int* work_counter;    // atomic work-item counter: replaces work_queue.cpp's ring + CAS pop
+    // ACCUM_SUM only, fused render + reduce-scatter of a multi-GPU group: a finished pixel's sum is stored straight into the
+    // staging slot of the rank that OWNS its part of the image (NVLink peer memory) instead of the local target.
+    // scatter_stage[o] = owner o's stage + this rank's slot; scatter_gpo = SoA8 groups per owner (0 = off)
+    float* scatter_stage[kMaxScatterRanks];
+    int scatter_gpo;
     const int* item_order; // optional: the k-th pulled work item is item_order[k] (expensive items first: see b200pt_capi.cu)
     DeviceCounters* counters;
     cudaTextureObject_t env;  // RGBA32F linear texture, texel t = reference float index 3t

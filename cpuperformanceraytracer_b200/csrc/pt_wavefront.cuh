@@ -116,6 +116,10 @@ pt_render_sorted_kernel(const __grid_constant__ RenderParams p, const __grid_con
                     }
                 } else {  // the pixel is finished: its slot is free again
                     float* px = p.target + S.addr[slot];
+                    if (ACCUM == kAccumSum && p.scatter_gpo > 0) {  // fused reduce-scatter: see pt_render_kernel
+                        const int a = S.addr[slot], g = a / 24, owner = g / p.scatter_gpo;
+                        px = p.scatter_stage[owner] + (size_t)(g - owner * p.scatter_gpo) * 24 + (a - g * 24);
+                    }
                     px[0] = avg.x;
                     px[8] = avg.y;
                     px[16] = avg.z;
@@ -152,9 +156,10 @@ pt_render_sorted_kernel(const __grid_constant__ RenderParams p, const __grid_con
                     const int yflip = p.height - 1 - y;
                     const int a = g * 24 + (lane & 7);
                     const float* px = p.target + a;
-                    S.avg[0][slot] = px[0];
-                    S.avg[1][slot] = px[8];
-                    S.avg[2][slot] = px[16];
+                    const bool from_zero = ACCUM == kAccumSum && p.scatter_gpo > 0;
+                    S.avg[0][slot] = from_zero ? 0.f : px[0];
+                    S.avg[1][slot] = from_zero ? 0.f : px[8];
+                    S.avg[2][slot] = from_zero ? 0.f : px[16];
                     S.frame[slot] = p.first_frame;
                     S.pixel[slot] = (uint32_t)x | ((uint32_t)yflip << 16);
                     S.addr[slot] = a;

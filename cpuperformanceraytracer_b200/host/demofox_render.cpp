@@ -58,7 +58,8 @@ b200pt_group* group_for(int profile)
     const int n = g_options.num_gpus > 16 ? 16 : g_options.num_gpus;
     for (int i = 0; i < n; i++) devices[i] = g_options.device + i;
     const int rc = b200pt_group_create(&p, devices, n, g_options.sharding ? B200PT_SHARD_TILES : B200PT_SHARD_SPP,
-                                       g_options.combine ? B200PT_COMBINE_PEER : B200PT_COMBINE_NCCL, &g_group[profile]);
+                                       g_options.combine == 2 ? B200PT_COMBINE_FUSED : (g_options.combine ? B200PT_COMBINE_PEER : B200PT_COMBINE_NCCL),
+                                       &g_group[profile]);
     if (rc != B200PT_OK) die("b200pt_group_create (num_gpus B200s are required; there is no CPU fallback)", nullptr, rc);
     return g_group[profile];
 }

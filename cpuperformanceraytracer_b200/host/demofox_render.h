@@ -52,7 +52,7 @@ struct B200RenderOptions {
     // device .. device + num_gpus - 1 of this process (b200pt_group_*, include/b200pt.h).
     int num_gpus = 1;
     int sharding = 0;             // 0 = frames of a ...Frames call (spp), 1 = tiles of every frame (bit-identical to 1 GPU)
-    int combine = 0;              // spp: 0 = NCCL reduce, 1 = the library's own kernel over NVLink peer memory
+    int combine = 0;              // spp: 0 = NCCL reduce, 1 = the library's own kernel over NVLink peer memory, 2 = fused into the render kernel
 };
 // must be called before the first render call of a variant (the contexts are created lazily)
 void B200SetRenderOptions(const B200RenderOptions& options);

@@ -7,7 +7,7 @@
 //   render_offline [--variant v4|v2|simt|v3redo|v3redo0] [--width W --height H --tiles-x X --tiles-y Y]
 //                  [--frames N] [--bounces B] [--env file.hdr | --cubemap px nx py ny pz nz]
 //                  [--bilinear] [--fast] [--per-frame-calls] [--out out.bmp] [--dump-f32 file]
-//                  [--gpus N [--shard spp|tiles] [--combine nccl|peer]] [--device D]
+//                  [--gpus N [--shard spp|tiles] [--combine nccl|peer|fused]] [--device D]
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -43,7 +43,7 @@ int main(int argc, char** argv)
         else if (a == "--gpus") opt.num_gpus = atoi(next());
         else if (a == "--device") opt.device = atoi(next());
         else if (a == "--shard") opt.sharding = std::string(next()) == "tiles" ? 1 : 0;
-        else if (a == "--combine") opt.combine = std::string(next()) == "peer" ? 1 : 0;
+        else if (a == "--combine") { const std::string v = next(); opt.combine = v == "peer" ? 1 : (v == "fused" ? 2 : 0); }
         else if (a == "--out") out = next();
         else if (a == "--dump-f32") dump = next();
         else { std::fprintf(stderr, "unknown argument %s\n", a.c_str()); return 2; }

@@ -271,10 +271,15 @@ int b200pt_scale_target_span(b200pt_context* ctx, size_t float_offset, size_t fl
  *   B200PT_COMBINE_NCCL ncclReduce(sum, root 0) over NVLink + one scale kernel on rank 0
  *   B200PT_COMBINE_PEER one kernel per GPU over NVLink peer memory: rank r sums slice r of all N buffers in
  *                       rank order (deterministic), scales, and stores the slice straight into rank 0's buffer
+ *   B200PT_COMBINE_FUSED render and reduce-scatter in ONE kernel: the render kernel stores every finished pixel's sum straight
+ *                       into a staging slot on the GPU that owns that part of the image (remote stores over NVLink, spread
+ *                       over the whole launch), so when the renders end only a LOCAL sum of N slots is left on each owner
+ *                       (rank order: deterministic) plus the store of its slice into rank 0's buffer.  Costs one extra
+ *                       image-sized buffer per GPU; at most 16 ranks.
  * libnccl.so.2 is loaded on first use (dlopen); without it B200PT_COMBINE_NCCL fails with B200PT_ERR_NOT_READY. */
 typedef struct b200pt_group b200pt_group;
 enum { B200PT_SHARD_SPP = 0, B200PT_SHARD_TILES = 1 };
-enum { B200PT_COMBINE_NCCL = 0, B200PT_COMBINE_PEER = 1 };
+enum { B200PT_COMBINE_NCCL = 0, B200PT_COMBINE_PEER = 1, B200PT_COMBINE_FUSED = 2 };
 /* params->device is ignored (devices[] rules); params->accum_mode is chosen by the sharding */
 int b200pt_group_create(const b200pt_params* params, const int32_t* devices, int32_t num_devices, int32_t sharding,
                         int32_t combine, b200pt_group** out_group);

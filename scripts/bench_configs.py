@@ -97,6 +97,7 @@ elif args.config == 3:
             n = args.group
             for sharding, combine, label in ((api.SHARD_SPP, api.COMBINE_NCCL, "spp-shard, NCCL reduce"),
                                              (api.SHARD_SPP, api.COMBINE_PEER, "spp-shard, peer-memory combine kernel"),
+                                             (api.SHARD_SPP, api.COMBINE_FUSED, "spp-shard, fused render + reduce-scatter"),
                                              (api.SHARD_TILES, api.COMBINE_PEER, "tile-shard, interleaved tiles + gather kernel")):
                 with api.Group(list(range(n)), sharding=sharding, combine=combine, profile=prof, math_mode=MATH, num_bounces=bounces, **kw) as G:
                     G.set_env(env); G.resize(W, H, ntx, nty)
@@ -177,9 +178,10 @@ elif args.config == 5:
     if args.group:
         n = args.group
         for sharding, combine, bands, label in ((api.SHARD_SPP, api.COMBINE_NCCL, 1, "spp-shard, NCCL reduce after the render"),
-                                                (api.SHARD_SPP, api.COMBINE_NCCL, 0, "spp-shard, NCCL reduce per band behind the render"),
+                                                (api.SHARD_SPP, api.COMBINE_NCCL, 8, "spp-shard, NCCL reduce per band behind the render"),
                                                 (api.SHARD_SPP, api.COMBINE_PEER, 1, "spp-shard, peer-memory combine kernel after the render"),
-                                                (api.SHARD_SPP, api.COMBINE_PEER, 0, "spp-shard, peer-memory combine kernel per band behind the render"),
+                                                (api.SHARD_SPP, api.COMBINE_PEER, 8, "spp-shard, peer-memory combine kernel per band behind the render"),
+                                                (api.SHARD_SPP, api.COMBINE_FUSED, 1, "spp-shard, fused render + reduce-scatter"),
                                                 (api.SHARD_TILES, api.COMBINE_PEER, 1, "tile-shard, interleaved tiles + gather kernel")):
             with api.Group(list(range(n)), sharding=sharding, combine=combine, profile=api.PROFILE_V2, math_mode=MATH, num_bounces=16) as G:
                 G.resize(W, H, ntx, nty)

@@ -76,10 +76,13 @@ def test_tile_shard_group_is_bit_identical(oracle, label, devices):
         assert np.array_equal(ldr, r.resolve_ldr())
 
 
+@pytest.mark.parametrize("combine", [api.COMBINE_PEER, api.COMBINE_FUSED], ids=["peer", "fused"])
 @pytest.mark.parametrize("label,devices", _device_sets(), ids=[s[0] for s in _device_sets()])
-def test_spp_shard_group_peer_combine(label, devices):
+def test_spp_shard_group_peer_combine(label, devices, combine):
+    """the library's own combines: a kernel that reads every rank's SUM buffer over peer memory (PEER), or render kernels that
+    scatter their sums to the owners' staging slots while they run + a local finish (FUSED)"""
     seq = _sequential([24, 9])
-    with api.Group(devices, sharding=api.SHARD_SPP, combine=api.COMBINE_PEER, profile=api.PROFILE_V2, num_bounces=BOUNCES) as g:
+    with api.Group(devices, sharding=api.SHARD_SPP, combine=combine, profile=api.PROFILE_V2, num_bounces=BOUNCES) as g:
         g.resize(W, H, NTX, NTY)
         g.render_frames(24)
         a = g.download_target()
@@ -92,7 +95,7 @@ def test_spp_shard_group_peer_combine(label, devices):
         g.render_frames(24)
         assert np.array_equal(g.download_target(), a)
         # band-pipelined: the combine of a band of tile rows runs while the next band renders -- same sums, same order
-        for bands in (2, 4, 9):
+        for bands in (2, 4, 9):  # (the fused combine has no bands: the exchange is already spread over the launch)
             g.set_bands(bands)
             g.reset()
             g.render_frames(24)
@@ -159,9 +162,10 @@ def test_group_with_env_profile(oracle):
     seq = _sequential([10], profile=api.PROFILE_OPT_V4, env=env, env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM)[0]
     o, _ = oracle.render(2, W, H, NTX, NTY, BOUNCES, 10, env=env, env_kind=2, env_sampler=2)
     assert np.array_equal(seq, o)
-    for sharding in (api.SHARD_TILES, api.SHARD_SPP):
-        with api.Group([0, 0], sharding=sharding, combine=api.COMBINE_PEER, profile=api.PROFILE_OPT_V4, num_bounces=BOUNCES,
-                       env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM) as g:
+    for sharding, combine, sched in ((api.SHARD_TILES, api.COMBINE_PEER, api.SCHED_DEFAULT), (api.SHARD_SPP, api.COMBINE_PEER, api.SCHED_DEFAULT),
+                                     (api.SHARD_SPP, api.COMBINE_FUSED, api.SCHED_DEFAULT), (api.SHARD_SPP, api.COMBINE_FUSED, api.SCHED_SORTED)):
+        with api.Group([0, 0], sharding=sharding, combine=combine, profile=api.PROFILE_OPT_V4, num_bounces=BOUNCES,
+                       env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM, scheduler=sched) as g:
             g.set_env(env)
             g.resize(W, H, NTX, NTY)
             g.render_frames(10)

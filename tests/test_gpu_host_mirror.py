@@ -125,7 +125,7 @@ def test_render_offline_multi_gpu(oracle, tmp_path):
     o, _ = oracle.render(oracle.PROFILE_V2, W, H, NTX, NTY, 8, 24 + 2)
     g, out = run_cli(tmp_path, "--variant", "v2", "--bounces", 8, "--gpus", n, "--shard", "tiles", frames=24, name="tiles")
     assert np.array_equal(g, o) and "Cross-GPU combine step" in out
-    for combine in ("nccl", "peer"):
+    for combine in ("nccl", "peer", "fused"):
         g, _ = run_cli(tmp_path, "--variant", "v2", "--bounces", 8, "--gpus", n, "--shard", "spp", "--combine", combine, frames=24,
                        name="spp_" + combine)
         assert np.allclose(g, o, rtol=3e-6, atol=3e-6)
