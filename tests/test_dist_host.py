@@ -58,6 +58,16 @@ def _worker(rank, world, port, total_frames, npix, out_dir):
         buf += _fake_radiance(npix, f)
     ptdist.reduce_sum_(buf)
     buf *= ptdist.finalize_scale(total_frames)
+    # continued job (SppShardedRenderer.render(resume=True)): rank 0 holds the average after F frames, turns it back into a sum
+    # (x (F + 1)), the other ranks start from zero, `more` further frames are sharded, reduced and scaled by 1/(F + more + 1)
+    F, more = total_frames, 5
+    cont = buf.clone() * float(F + 1) if rank == 0 else torch.zeros(npix * 3, dtype=torch.float32)
+    sh2 = ptdist.shard_frames(more, world, rank, first_frame=F + 1)
+    for f in range(sh2.first_frame, sh2.first_frame + sh2.nframes):
+        cont += _fake_radiance(npix, f)
+    ptdist.reduce_sum_(cont)
+    cont *= ptdist.finalize_scale(F + more)
+    np.save(os.path.join(out_dir, f"cont_{rank}.npy"), cont.numpy())
     # tile-shard: every rank fills its own contiguous span, all_gather reassembles
     W, H, nty = 16, 8, 4
     ts = ptdist.shard_tile_rows(W, H, nty, world, rank)
@@ -84,6 +94,13 @@ def test_gloo_world2_spp_reduce_and_tile_gather(tmp_path):
     a, b = np.load(tmp_path / "spp_0.npy"), np.load(tmp_path / "spp_1.npy")
     assert np.array_equal(a, b)  # every rank ends with the same image
     assert np.allclose(a, seq, rtol=1e-6, atol=1e-7)
+    # the continued job equals the reference's running average run over all 14 frames in order
+    avg = np.zeros(npix * 3, dtype=np.float32)
+    for f in range(1, total_frames + 5 + 1):
+        c = _fake_radiance(npix, f).numpy()
+        avg = avg + (c - avg) * np.float32(1.0 / (f + 1.0))
+    c0 = np.load(tmp_path / "cont_0.npy")
+    assert np.array_equal(c0, np.load(tmp_path / "cont_1.npy")) and np.allclose(c0, avg, rtol=2e-6, atol=2e-7)
     t0, t1 = np.load(tmp_path / "tile_0.npy"), np.load(tmp_path / "tile_1.npy")
     assert np.array_equal(t0, np.arange(16 * 8 * 3, dtype=np.float32)) and np.array_equal(t0, t1)
 
