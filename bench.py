@@ -383,6 +383,7 @@ def main():
         return v
 
     segs, escs, culled = delta("segments"), delta("escapes"), delta("culled_segments")
+    ffma_peak = r.measure_fp32_peak() if rank == 0 else None  # FFMA micro-benchmark, outside the timed region
     paths_per_step = WIDTH * HEIGHT * spp
     total_paths = paths_per_step * args.steps
     value = total_paths / (total_ms * 1e-3) * 1e-6
@@ -529,6 +530,8 @@ def main():
                                "kernel), whose trace the kernel skips; executed_fp32_frac etc. under `ncu`: what the hardware "
                                "executed, from the committed ncu capture",
             "culled_segment_share": culled / segs if segs else None,
+            "measured_ffma_peak_tflops_per_gpu": ffma_peak,
+            "frac_vs_measured_ffma_peak": (achieved / (ffma_peak * world)) if ffma_peak else None,
             "ncu": measured_ncu_utilisation(),
             "traffic": traffic, "traffic_source": traffic_src,
             "peak_source": f"148 SMs x 128 FP32 lanes x 2 x sm_max_mhz {peaks['sm_max_mhz']:.0f} MHz "

@@ -29,7 +29,7 @@ ABI_SYMBOLS = [
     "b200pt_download_target", "b200pt_render_host", "b200pt_resolve_ldr", "b200pt_bind_device_target",
     "b200pt_get_device_target", "b200pt_set_stream", "b200pt_finalize_sum", "b200pt_download_rng_state",
     "b200pt_get_counters", "b200pt_compute_cull_rects", "b200pt_set_tile_row_range", "b200pt_set_tile_range", "b200pt_set_tile_stride", "b200pt_present_submit", "b200pt_present_acquire", "b200pt_present_blocking", "b200pt_set_scene_v4", "b200pt_compute_cull_rects_scene_v4", "b200pt_set_scene_cornell", "b200pt_compute_cull_rects_scene_cornell",
-    "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_scale_target", "b200pt_scale_target_span",
+    "b200pt_eval_portable", "b200pt_check_portable_tiers", "b200pt_static_tables_match", "b200pt_measure_fp32_peak", "b200pt_scale_target", "b200pt_scale_target_span",
     "b200pt_group_create", "b200pt_group_destroy", "b200pt_group_size", "b200pt_group_context", "b200pt_group_set_env",
     "b200pt_group_resize", "b200pt_group_reset", "b200pt_group_set_bands", "b200pt_group_set_frame_counter", "b200pt_group_get_frame_counter",
     "b200pt_group_render_frames", "b200pt_group_synchronize", "b200pt_group_upload_target", "b200pt_group_download_target",
@@ -116,6 +116,7 @@ def load_library():
                                               ctypes.POINTER(ctypes.c_uint64)]
     L.b200pt_compute_cull_rects.argtypes = [ctypes.c_int, i32, i32, ctypes.POINTER(ctypes.c_float), ctypes.POINTER(i32)]
     L.b200pt_scale_target.argtypes = [vp, ctypes.c_float]
+    L.b200pt_measure_fp32_peak.argtypes = [vp, ctypes.POINTER(ctypes.c_double)]
     L.b200pt_scale_target_span.argtypes = [vp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_float, vp]
     # several GPUs of one process
     L.b200pt_group_create.argtypes = [ctypes.POINTER(Params), ctypes.POINTER(i32), i32, i32, i32, ctypes.POINTER(vp)]
@@ -346,6 +347,12 @@ class Renderer:
                                                    ctypes.byref(bad), ctypes.byref(lit))
         self._check(rc, "b200pt_check_portable_tiers")
         return bad.value, lit.value
+
+    def measure_fp32_peak(self):
+        """FFMA micro-benchmark on this GPU: TFLOP/s (FFMA = 2 flop)"""
+        t = ctypes.c_double()
+        self._check(self._lib.b200pt_measure_fp32_peak(self._ctx, ctypes.byref(t)), "b200pt_measure_fp32_peak")
+        return t.value
 
     def counters(self):
         c = Counters()

@@ -979,6 +979,40 @@ int b200pt_check_portable_tiers(b200pt_context* c, int fn, uint64_t first, uint6
     return B200PT_OK;
 }
 
+int b200pt_measure_fp32_peak(b200pt_context* c, double* tflops)
+{
+    if (!c || !tflops) return B200PT_ERR_INVALID_ARGUMENT;
+    DeviceGuard guard(c->device);
+    CUDA_TRY(c, guard.status);
+    const int blocks = c->sm_count * 4, iters = 4096;
+    float* scratch = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    cudaError_t e = cudaMalloc(&scratch, (size_t)blocks * 256 * sizeof(float));
+    if (e == cudaSuccess) e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    double best = 0.0;
+    for (int rep = 0; rep < 4 && e == cudaSuccess; rep++) {  // first trip warms the clocks up
+        e = cudaEventRecord(e0, c->stream);
+        if (e == cudaSuccess) e = launch_ffma_peak(scratch, blocks, iters, c->stream);
+        if (e == cudaSuccess) e = cudaEventRecord(e1, c->stream);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0.f;
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, e0, e1);
+        if (e == cudaSuccess && ms > 0.f) {
+            const double flops = (double)blocks * 256.0 * (double)iters * 256.0 * 2.0;
+            const double t = flops / (ms * 1e-3) * 1e-12;
+            if (t > best) best = t;
+        }
+    }
+    c->launches += 4;
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    cudaFree(scratch);
+    CUDA_TRY(c, e);
+    *tflops = best;
+    return B200PT_OK;
+}
+
 int b200pt_static_tables_match(int profile)
 {
     switch (profile) {

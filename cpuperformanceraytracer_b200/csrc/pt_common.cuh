@@ -248,6 +248,7 @@ cudaError_t occupancy_sorted_fast(const LaunchConfig& lc, int* blocks_per_sm);
 cudaError_t launch_resolve_ldr(const float* target, uint32_t* out, int width, int height, int tile_w, int tile_h,
                                int num_tiles_x, int mode, cudaStream_t stream);
 cudaError_t launch_scale(float* target, size_t n, float scale, cudaStream_t stream);
+cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t stream);
 cudaError_t launch_build_item_order(const RenderParams& rp, int* order, cudaStream_t stream);
 cudaError_t launch_tile_gather(const float* src, float* dst, int num_tiles, int mod, int rem, size_t floats_per_tile, int sm_count,
                                cudaStream_t stream);

@@ -175,6 +175,34 @@ cudaError_t launch_tile_gather(const float* src, float* dst, int num_tiles, int 
     return cudaGetLastError();
 }
 
+// FFMA micro-benchmark: the measured FP32-pipe peak the roofline of K1 is quoted against (SURVEY.md 8d asks for the real
+// sustained FP32 rate instead of lanes x nominal clock).  16 independent fused multiply-add chains per thread, 4 CTAs of 256
+// threads per SM, `iters` trips of 16 x 16 FFMA: 2 flop each.
+__global__ void __launch_bounds__(256) ffma_peak_kernel(float* __restrict__ out, int iters, float seed)
+{
+    float a[16];
+#pragma unroll
+    for (int k = 0; k < 16; k++) a[k] = seed + (float)(threadIdx.x + k);
+    const float m = 1.0000001f, c = seed * 1e-9f;
+    for (int i = 0; i < iters; i++) {
+#pragma unroll
+        for (int r = 0; r < 16; r++) {
+#pragma unroll
+            for (int k = 0; k < 16; k++) a[k] = __fmaf_rn(a[k], m, c);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 16; k++) s += a[k];
+    if (s == 123.456f) out[blockIdx.x * blockDim.x + threadIdx.x] = s;  // never true: keeps the chains alive
+}
+
+cudaError_t launch_ffma_peak(float* scratch, int blocks, int iters, cudaStream_t stream)
+{
+    ffma_peak_kernel<<<blocks, 256, 0, stream>>>(scratch, iters, 1.0f);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_resolve_ldr(const float* target, uint32_t* out, int width, int height, int tile_w, int tile_h,
                                int num_tiles_x, int mode, cudaStream_t stream)
 {

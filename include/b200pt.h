@@ -327,6 +327,10 @@ int b200pt_set_scene_cornell(b200pt_context* ctx, const b200pt_quad* quads /* 6 
 int b200pt_compute_cull_rects_scene_cornell(const b200pt_quad* quads, const b200pt_sphere* spheres, int32_t width, int32_t height,
                                             float* rects, int32_t* count);
 
+/* measurement hook: the FP32-pipe peak of this GPU as an FFMA micro-benchmark achieves it (TFLOP/s, FFMA = 2 flop; best of 4
+ * launches of ~1e12 flop) -- the measured denominator next to the nominal 148 SMs x 128 lanes x 2 x clock */
+int b200pt_measure_fp32_peak(b200pt_context* ctx, double* tflops);
+
 /* debug/parity hook: u32 RNG state of every pixel after the last rendered frame's path ended
  * (row-major W*H, row 0 = top); checks wang_hash stream parity bit for bit */
 int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
