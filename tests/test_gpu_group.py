@@ -192,6 +192,32 @@ def test_spp_shard_group_nccl():
         assert np.allclose(g.download_target(), seq[0], rtol=3e-6, atol=3e-6)
 
 
+def test_group_at_baseline_image_sizes(oracle):
+    """BASELINE geometry: 1920x1080 tiles 10x15 (config 2) against the oracle, 4096x4096 tiles 16x64 (config 5's tiling at a
+    quarter of its pixels) against one context: interleaved tiles bit-identical, fused / peer spp combine within 3e-6"""
+    devices = list(range(min(_ngpus(), 8))) if _ngpus() >= 2 else [0, 0, 0]
+    w, h, ntx, nty, frames = 1920, 1080, 10, 15, 4
+    o, _ = oracle.render(0, w, h, ntx, nty, BOUNCES, frames)
+    with api.Group(devices, sharding=api.SHARD_TILES, profile=api.PROFILE_V2, num_bounces=BOUNCES) as g:
+        g.resize(w, h, ntx, nty)
+        g.render_frames(frames)
+        assert np.array_equal(g.download_target(), o)
+    w, h, ntx, nty, frames = 4096, 4096, 16, 64, 3
+    with api.Renderer(profile=api.PROFILE_V2, num_bounces=16) as r:
+        r.resize(w, h, ntx, nty)
+        r.render_frames(frames)
+        seq = r.download_target()
+    with api.Group(devices, sharding=api.SHARD_TILES, profile=api.PROFILE_V2, num_bounces=16) as g:
+        g.resize(w, h, ntx, nty)
+        g.render_frames(frames)
+        assert np.array_equal(g.download_target(), seq)
+    for combine in (api.COMBINE_FUSED, api.COMBINE_PEER):
+        with api.Group(devices, sharding=api.SHARD_SPP, combine=combine, profile=api.PROFILE_V2, num_bounces=16) as g:
+            g.resize(w, h, ntx, nty)
+            g.render_frames(frames)
+            assert np.allclose(g.download_target(), seq, rtol=3e-6, atol=3e-6)
+
+
 def test_group_argument_checking():
     import ctypes
     lib = api.load_library()
