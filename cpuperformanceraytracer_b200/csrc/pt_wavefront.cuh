@@ -45,8 +45,13 @@ template <int PROFILE> struct WfShared {
     int cls[2][8];                             // paths per role of the current trip (double-buffered by trip parity)
 };
 
+// the sorted kernel keeps the round-2 launch bounds it was measured with (4 CTAs per SM for the v4 / v3_redo families)
+template <int PROFILE> struct MinBlocksSorted {
+    static constexpr int value = (PROFILE == kProfileV4 || is_v3redo(PROFILE)) ? 4 : B200PT_MIN_BLOCKS_CORNELL;
+};
+
 template <int PROFILE, int ENVK, int ENVS, int ACCUM, bool STATIC, class M>
-__global__ void __launch_bounds__(kWfThreads, MinBlocks<PROFILE>::value)
+__global__ void __launch_bounds__(kWfThreads, MinBlocksSorted<PROFILE>::value)
 pt_render_sorted_kernel(const __grid_constant__ RenderParams p, const __grid_constant__ typename SceneOf<PROFILE>::type scene)
 {
     constexpr int kFields = WfShared<PROFILE>::kFields;
