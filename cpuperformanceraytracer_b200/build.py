@@ -29,7 +29,8 @@ COMMON = ["-std=c++17", "-O3", "-lineinfo", "--extended-lambda", "-Xcompiler", "
           "-ffp-contract=off", "-I", os.path.join(ROOT, "include")]
 IEEE = ["--fmad=false", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
 # tuning knob for experiments: minimum resident CTAs per SM handed to __launch_bounds__
-for _knob in ("B200PT_MIN_BLOCKS_CORNELL", "B200PT_MIN_BLOCKS_V4", "B200PT_MIN_BLOCKS_V3REDO"):
+for _knob in ("B200PT_MIN_BLOCKS_CORNELL", "B200PT_MIN_BLOCKS_V4", "B200PT_MIN_BLOCKS_V3REDO", "B200PT_THREADS_CORNELL", "B200PT_THREADS_V4",
+              "B200PT_THREADS_V3REDO"):
     if os.environ.get(_knob):
         COMMON = COMMON + ["-D%s=%s" % (_knob, os.environ[_knob])]
 

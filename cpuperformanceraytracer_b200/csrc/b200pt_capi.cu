@@ -43,7 +43,7 @@ LaunchConfig launch_config(const b200pt_context* c)
     if (lc.static_scene && (lc.profile == kProfileV2 || lc.profile == kProfileSimtTextured) &&
         !cornell_spheres_match_static_tables(c->scenes.cornell.sphere))
         lc.static_scene = 0;
-    lc.block = 256;
+    lc.block = block_threads_for_profile(lc.profile);  // the sorted kernel always runs 256 threads (kWfThreads)
     lc.grid = 1;
     return lc;
 }
@@ -582,10 +582,10 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
 
     LaunchConfig lc = launch_config(c);
     // persistent grid: every SM holds blocks_per_sm resident CTAs; warps pull 32-pixel items
-    const int warps_per_block = lc.block / 32;
-    const int max_useful_blocks = (rp.num_items + warps_per_block - 1) / warps_per_block;
     // the sorted kernel packs the bounce count into 8 bits and the pixel coordinates into 16 each
     const bool sorted = c->sorted && rp.num_bounces <= 250 && rp.width <= 65535 && rp.height <= 65535;
+    const int warps_per_block = (sorted ? 256 : lc.block) / 32;
+    const int max_useful_blocks = (rp.num_items + warps_per_block - 1) / warps_per_block;
     lc.grid = c->sm_count * (sorted ? c->blocks_per_sm_sorted : c->blocks_per_sm);
     if (lc.grid > max_useful_blocks) lc.grid = max_useful_blocks;
     if (lc.grid < 1) lc.grid = 1;

@@ -221,6 +221,21 @@ enum : int { kEnvNone = 0, kEnvEquirect = 1, kEnvCubemap = 2 };
 enum : int { kSamplerPoint = 0, kSamplerBilinear = 1, kSamplerRandom = 2 };
 enum : int { kAccumAverage = 0, kAccumSum = 1 };
 
+// threads per CTA of pt_render_kernel, per kernel family (tuning knobs; multiples of 32)
+#ifndef B200PT_THREADS_CORNELL
+#define B200PT_THREADS_CORNELL 256
+#endif
+#ifndef B200PT_THREADS_V4
+#define B200PT_THREADS_V4 256
+#endif
+#ifndef B200PT_THREADS_V3REDO
+#define B200PT_THREADS_V3REDO 256
+#endif
+__host__ __device__ constexpr int block_threads_for_profile(int profile)
+{
+    return profile == kProfileV4 ? B200PT_THREADS_V4 : (is_v3redo(profile) ? B200PT_THREADS_V3REDO : B200PT_THREADS_CORNELL);
+}
+
 struct LaunchConfig {
     int profile, env_kind, env_sampler, accum_mode;
     int static_scene;  // Cornell profiles: vertex coordinates as immediates (same bits, fewer instructions)

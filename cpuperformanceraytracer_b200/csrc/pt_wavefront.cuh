@@ -36,7 +36,7 @@ constexpr int kCulledFramesPerTrip = 3;  // a camera-culled pixel never traces: 
 template <int PROFILE> struct WfShared {
     static constexpr int kFields = (PROFILE == kProfileV4 || is_v3redo(PROFILE)) ? kV4MatFields : kLegacyMatFields;
     float smat[kFields * kMatStride];
-    typename SharedOf<PROFILE>::type trace;  // Cornell-family trace: variant table + per-thread candidate stacks
+    typename SharedOf<PROFILE, kWfThreads>::type trace;  // Cornell-family trace: variant table + per-thread candidate stacks
     uint4 rec[kWfRecordQuads][kWfThreads];     // the sort's transit records (128-bit accesses, consecutive threads)
     float avg[3][kWfThreads];                  // per pixel slot: running average (or sum)
     int frame[kWfThreads];                     //                 next frame to fold
