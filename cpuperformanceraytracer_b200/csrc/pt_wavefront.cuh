@@ -8,12 +8,16 @@
 // Here a path is NOT tied to a lane.  One loop trip of a CTA is
 //     A  per-role work      shade a hit | env lookup + fold + start the pixel's next path      (role-pure warps)
 //     B  scene trace        every live path, whatever its role was                             (full warps)
-//     C  sort               every thread writes its path record to shared memory at the position its role gives it
-//                           (ballot + popc inside the warp, one 40-entry prefix over roles x warps), __syncthreads,
-//                           and reads the record at its own thread index
+//     C  sort               every thread writes its path record (5 x 16 bytes) to shared memory at the position its role
+//                           gives it (ballots inside the warp, one shared-memory atomicAdd per role and warp, the role
+//                           totals after a __syncthreads), __syncthreads, and reads the record at its own thread index
 // so after C the threads [0, n0) hold the paths to shade, [n0, n1) the ones that also end at the bounce limit,
 // [n1, n2) the misses, [n2, n3) the misses of camera-culled pixels (no trace either), and the rest are idle: at most
 // one warp per role boundary is mixed.  A warp whose 32 threads are idle pulls the next 32-pixel work item.
+//
+// Measured on B200 (profiles/r02_a_*): 27.1 (v2) / 24.3 (v4) active lanes per instruction against 21.3 /
+// 17.2 for pt_render_kernel, and 17 % / 4 % SLOWER: the sort costs 20-25 % of the issued instructions and its two barriers
+// per trip take 10 points of issue-slot utilisation.  It is selectable (B200PT_SCHED_SORTED), not the default.
 //
 // What stays per pixel lives in shared memory, indexed by a slot number that travels with the path: the running
 // average, the frame counter, the pixel coordinates.  One path per pixel is in flight at any time, so a pixel's
