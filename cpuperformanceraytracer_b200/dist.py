@@ -172,6 +172,33 @@ class SppShardedRenderer:
         self.r.frame_counter = last
         return self.buf
 
+    def render_host_slices(self, host_state, total_frames):
+        """The reference-facing call for N ranks whose caller keeps its accumulation buffer in host memory that EVERY rank
+        can address (POSIX shared memory, page-locked in each process): rank r moves only floats [lo_r, hi_r) of it, over
+        its own PCIe link, in both directions.  The caller's state enters the sum exactly once (each slice is uploaded by
+        exactly one rank, the rest of every SUM buffer starts at zero); after the all-reduce every rank holds the finished
+        image and writes its slice back.  host_state: a CPU float32 tensor of W*H*3 elements, the same memory on all
+        ranks.  Blocks until this rank's slice is in host memory."""
+        torch = self.torch
+        n = self.buf.numel()
+        base, rem = divmod(n // 4, self.world)  # float4-aligned slices
+        lo = 4 * (self.rank * base + min(self.rank, rem))
+        hi = lo + 4 * (base + (1 if self.rank < rem else 0))
+        sh = shard_frames(total_frames, self.world, self.rank, 1)
+        with torch.cuda.stream(self.stream):
+            self.buf.zero_()
+            if hi > lo:
+                self.buf[lo:hi].copy_(host_state[lo:hi], non_blocking=True)
+            self.r.frame_counter = sh.first_frame - 1
+            self.r.render_frames(sh.nframes, sync=False)
+            reduce_sum_(self.buf)
+            self.r.finalize_sum(total_frames)
+            if hi > lo:
+                host_state[lo:hi].copy_(self.buf[lo:hi], non_blocking=True)
+        self.r.frame_counter = total_frames
+        self.stream.synchronize()
+        return lo, hi
+
     def close(self):
         self.r.close()
 
