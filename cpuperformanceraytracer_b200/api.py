@@ -18,7 +18,7 @@ MATH_PARITY, MATH_FAST = 0, 1
 ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
 SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
 ACCUM_RUNNING_AVERAGE, ACCUM_SUM = 0, 1
-LDR_FILE_RGBA, LDR_SCREEN_BGRA = 0, 1
+LDR_FILE_RGBA, LDR_SCREEN_BGRA, LDR_EXACT_ACES = 0, 1, 2
 SCHED_DEFAULT, SCHED_LANE, SCHED_SORTED = 0, 1, 2
 
 # every symbol include/b200pt.h declares (tests/test_abi.py checks the library exports them all)
@@ -51,7 +51,8 @@ class Params(ctypes.Structure):
                 ("math_mode", ctypes.c_int32), ("num_bounces", ctypes.c_int32), ("env_kind", ctypes.c_int32),
                 ("env_sampler", ctypes.c_int32), ("accum_mode", ctypes.c_int32), ("output_to_screen", ctypes.c_int32),
                 ("disable_camera_culling", ctypes.c_int32), ("generic_scene_tables", ctypes.c_int32),
-                ("scheduler", ctypes.c_int32), ("disable_item_order", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3)]
+                ("scheduler", ctypes.c_int32), ("disable_item_order", ctypes.c_int32), ("exact_exp", ctypes.c_int32),
+                ("sincos_unit_vectors", ctypes.c_int32), ("exact_aces_tonemap", ctypes.c_int32)]
 
 
 class Counters(ctypes.Structure):
@@ -161,7 +162,8 @@ class Renderer:
 
     def __init__(self, profile=PROFILE_V2, math_mode=MATH_PARITY, num_bounces=-1, device=0, env_kind=None,
                  env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False,
-                 disable_camera_culling=False, generic_scene_tables=False, scheduler=SCHED_DEFAULT, disable_item_order=False):
+                 disable_camera_culling=False, generic_scene_tables=False, scheduler=SCHED_DEFAULT, disable_item_order=False,
+                 exact_exp=False, sincos_unit_vectors=False, exact_aces_tonemap=False):
         self._lib = load_library()
         self._ctx = ctypes.c_void_p()
         p = default_params(profile)
@@ -171,6 +173,9 @@ class Renderer:
         p.generic_scene_tables = int(bool(generic_scene_tables))
         p.scheduler = int(scheduler)
         p.disable_item_order = int(bool(disable_item_order))
+        # global_preprocessor_flags.h:63-65, non-default side (0 = the reference's checked-in "fast" variants)
+        p.exact_exp, p.sincos_unit_vectors = int(bool(exact_exp)), int(bool(sincos_unit_vectors))
+        p.exact_aces_tonemap = int(bool(exact_aces_tonemap))
         if env_kind is not None:
             p.env_kind = env_kind
         if env_sampler is not None:
@@ -399,11 +404,14 @@ class Group:
     tiles (SHARD_TILES) of every render call are sharded over `devices`; the image lives on devices[0]."""
 
     def __init__(self, devices, sharding=SHARD_SPP, combine=COMBINE_NCCL, profile=PROFILE_V2, math_mode=MATH_PARITY,
-                 num_bounces=-1, env_kind=None, env_sampler=None, output_to_screen=False, scheduler=SCHED_DEFAULT):
+                 num_bounces=-1, env_kind=None, env_sampler=None, output_to_screen=False, scheduler=SCHED_DEFAULT,
+                 exact_exp=False, sincos_unit_vectors=False, exact_aces_tonemap=False):
         self._lib = load_library()
         self._g = ctypes.c_void_p()
         p = default_params(profile)
         p.math_mode, p.num_bounces = math_mode, num_bounces
+        p.exact_exp, p.sincos_unit_vectors = int(bool(exact_exp)), int(bool(sincos_unit_vectors))
+        p.exact_aces_tonemap = int(bool(exact_aces_tonemap))
         p.scheduler = int(scheduler)
         p.output_to_screen = int(bool(output_to_screen))
         if env_kind is not None:

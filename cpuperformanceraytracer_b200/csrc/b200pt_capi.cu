@@ -37,6 +37,7 @@ LaunchConfig launch_config(const b200pt_context* c)
                                                                                                               : kSamplerPoint;
     lc.accum_mode = c->params.accum_mode;
     lc.static_scene = (c->params.generic_scene_tables || c->custom_scene) ? 0 : 1;
+    if (lc.profile == kProfileV4 && (c->params.exact_exp || c->params.sincos_unit_vectors)) lc.static_scene = 0;  // non-default switches
     if (lc.profile == kProfileV4 && lc.static_scene && !v4_scene_matches_static_tables(c->scenes.v4)) lc.static_scene = 0;
     if (lc.static_scene && lc.profile == kProfileV3Redo && !v3redo_spheres_match_static_tables(c->scenes.v3redo.sphere)) lc.static_scene = 0;
     if (lc.static_scene && lc.profile == kProfileV3RedoS0 && !v3redo0_spheres_match_static_tables(c->scenes.v3redo0.sphere)) lc.static_scene = 0;
@@ -202,6 +203,8 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     if (params->profile < B200PT_PROFILE_V2 || params->profile > B200PT_PROFILE_V3_REDO_SCENE0) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->math_mode != B200PT_MATH_PARITY && params->math_mode != B200PT_MATH_FAST) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->accum_mode != B200PT_ACCUM_RUNNING_AVERAGE && params->accum_mode != B200PT_ACCUM_SUM) return B200PT_ERR_INVALID_ARGUMENT;
+    // the reference reads USE_FAST_APPROXIMATE_EXP / USE_UNIT_VECTOR_REJECTION_SAMPLING in the v4 source only
+    if (params->profile != B200PT_PROFILE_OPT_V4 && (params->exact_exp || params->sincos_unit_vectors)) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->profile == B200PT_PROFILE_OPT_V4) {
         if (params->env_kind < B200PT_ENV_NONE || params->env_kind > B200PT_ENV_CUBEMAP) return B200PT_ERR_INVALID_ARGUMENT;
         if (params->env_kind != B200PT_ENV_NONE && params->env_sampler != B200PT_SAMPLER_BILINEAR &&
@@ -514,7 +517,8 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     rp.target = c->d_target;
     rp.rng_out = c->d_rng;
     rp.screen = screen;
-    rp.screen_mode = B200PT_LDR_SCREEN_BGRA;
+    rp.screen_mode = B200PT_LDR_SCREEN_BGRA | (c->params.exact_aces_tonemap ? B200PT_LDR_EXACT_ACES : 0);
+    rp.v4_flags = (c->params.exact_exp ? 1 : 0) | (c->params.sincos_unit_vectors ? 2 : 0);
     rp.work_counter = c->d_work_counter;
     rp.counters = c->d_counters;
     rp.env = c->env_tex;
@@ -710,8 +714,9 @@ int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H
 
 int b200pt_resolve_ldr(b200pt_context* c, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter)
 {
-    if (!c || !host_dst || (mode != B200PT_LDR_FILE_RGBA && mode != B200PT_LDR_SCREEN_BGRA)) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c || !host_dst || (mode & ~(B200PT_LDR_SCREEN_BGRA | B200PT_LDR_EXACT_ACES))) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
+    if (c->params.exact_aces_tonemap) mode |= B200PT_LDR_EXACT_ACES;
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));  // the present ring may still be reading slot 0

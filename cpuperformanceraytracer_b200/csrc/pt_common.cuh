@@ -180,7 +180,8 @@ struct RenderParams {
     float* target;        // tile-major SoA8 accumulation buffer (RenderTile, v4.cpp:1189-1252)
     uint32_t* rng_out;    // optional: final RNG state per pixel, row-major (debug/parity)
     uint32_t* screen;     // optional: row-major u32 image, tone-mapped in the kernel tail (OUTPUT_TO_SCREEN)
-    int screen_mode;      // 0 = file packing, 1 = screen packing
+    int screen_mode;      // bit 0: 0 = file packing, 1 = screen packing; bit 1: exact ACES curve
+    int v4_flags;         // generic OPT_V4 kernels only: bit 0 exact exp, bit 1 sin/cos unit vectors (b200pt_params)
     int* work_counter;    // atomic work-item counter: replaces work_queue.cpp's ring + CAS pop
     // ACCUM_SUM only, fused render + reduce-scatter of a multi-GPU group: a finished pixel's sum is stored straight into the
     // staging slot of the rank that OWNS its part of the image (NVLink peer memory) instead of the local target.

@@ -28,22 +28,32 @@ __device__ __forceinline__ float aces(float X)  // v4.cpp:166-176
     const float rcpDenom = __frcp_rn(fmaf(X, fmaf(c, X, d), e));
     return saturate(__fmul_rn(__fmul_rn(X, fmaf(a, X, b)), rcpDenom));
 }
+__device__ __forceinline__ float aces_exact(float X)  // USE_FAST_APPROXIMATE_ACES_TONEMAP 0, v4.cpp:172-175: no fused operation, a true division
+{
+    const float a = 2.51f, b = 0.03f, c = 2.43f, d = 0.59f, e = 0.14f;
+    const float num = __fmul_rn(X, __fadd_rn(__fmul_rn(a, X), b));
+    const float den = __fadd_rn(__fmul_rn(X, __fadd_rn(__fmul_rn(c, X), d)), e);
+    return saturate(__fdiv_rn(num, den));
+}
 __device__ __forceinline__ float srgb(float v)  // v4.cpp:178-187
 {
     v = saturate(v);
     return (v < 0.0031308f) ? __fmul_rn(v, 12.92f) : fmaf(1.055f, fast_pow_gamma(v), -0.055f);
 }
-__device__ __forceinline__ uint32_t quantize(float c)
+__device__ __forceinline__ uint32_t quantize(float c, bool exact_aces)
 {
-    float v = srgb(aces(__fmul_rn(c, 1.0f)));  // c_exposure = 1
+    const float x = __fmul_rn(c, 1.0f);  // c_exposure = 1
+    float v = srgb(exact_aces ? aces_exact(x) : aces(x));
     v = __fmul_rn(saturate(v), 255.f);
     return (uint32_t)__float2int_rn(v) & 0xFFu;
 }
-// mode 0: file packing A=FF | B<<16 | G<<8 | R (v4.cpp:1321-1325); mode 1: screen R<<16 | G<<8 | B (:1285-1289)
+// mode bit 0: 0 = file packing A=FF | B<<16 | G<<8 | R (v4.cpp:1321-1325), 1 = screen R<<16 | G<<8 | B (:1285-1289)
+// mode bit 1 (B200PT_LDR_EXACT_ACES): the exact ACES curve instead of the fast one
 __device__ __forceinline__ uint32_t pack(float r, float g, float b, int mode)
 {
-    const uint32_t R = quantize(r), G = quantize(g), B = quantize(b);
-    return (mode == 0) ? (0xFF000000u | (B << 16) | (G << 8) | R) : ((R << 16) | (G << 8) | B);
+    const bool ex = (mode & 2) != 0;
+    const uint32_t R = quantize(r, ex), G = quantize(g, ex), B = quantize(b, ex);
+    return ((mode & 1) == 0) ? (0xFF000000u | (B << 16) | (G << 8) | R) : ((R << 16) | (G << 8) | B);
 }
 
 }  // namespace tonemap

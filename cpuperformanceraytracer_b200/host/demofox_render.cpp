@@ -37,6 +37,9 @@ b200pt_params params_for(int profile)
         p.env_kind = !g_options.use_env_map ? B200PT_ENV_NONE : (g_options.use_env_cubemap ? B200PT_ENV_CUBEMAP : B200PT_ENV_EQUIRECT);
         p.env_sampler = g_options.use_random_jitter_texture_sampling ? B200PT_SAMPLER_RANDOM : B200PT_SAMPLER_BILINEAR;
         p.output_to_screen = g_options.output_to_screen;
+        p.exact_exp = !g_options.use_fast_approximate_exp;
+        p.sincos_unit_vectors = !g_options.use_unit_vector_rejection_sampling;
+        p.exact_aces_tonemap = !g_options.use_fast_approximate_aces_tonemap;
     }
     return p;
 }

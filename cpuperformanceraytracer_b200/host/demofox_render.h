@@ -46,6 +46,10 @@ struct B200RenderOptions {
     int use_env_cubemap = USE_ENV_CUBEMAP;
     int use_random_jitter_texture_sampling = USE_RANDOM_JITTER_TEXTURE_SAMPLING;
     int output_to_screen = OUTPUT_TO_SCREEN;
+    // DemofoxRenderOptV4 only (the other variants' sources do not read them); 0 selects the exact variants
+    int use_fast_approximate_aces_tonemap = USE_FAST_APPROXIMATE_ACES_TONEMAP;
+    int use_fast_approximate_exp = USE_FAST_APPROXIMATE_EXP;
+    int use_unit_vector_rejection_sampling = USE_UNIT_VECTOR_REJECTION_SAMPLING;
     int v3_redo_scene = 1;        // `#define SCENE` of demofox_path_tracing_v3_redo.cpp:379 (1 = the checked-in choice, 0 = the Cornell box)
     // Several GPUs behind the same entry points: the reference fans a render call out to its worker threads below
     // DemofoxRenderOptV4 (..._optimization_v4.cpp:1696-1721); with num_gpus > 1 the call is sharded over devices

@@ -33,16 +33,16 @@
 #define ACCUMULATE_FRAMES 1  // :60 (always on in the kernel)
 #endif
 #ifndef USE_FAST_APPROXIMATE_GAMMA
-#define USE_FAST_APPROXIMATE_GAMMA 1  // :62 (the only variant implemented)
+#define USE_FAST_APPROXIMATE_GAMMA 1  // :62 (the only variant implemented: pow_ps is an MSVC SVML routine)
 #endif
 #ifndef USE_FAST_APPROXIMATE_ACES_TONEMAP
-#define USE_FAST_APPROXIMATE_ACES_TONEMAP 1  // :63 (the only variant implemented)
+#define USE_FAST_APPROXIMATE_ACES_TONEMAP 1  // :63
 #endif
 #ifndef USE_FAST_APPROXIMATE_EXP
-#define USE_FAST_APPROXIMATE_EXP 1  // :64 (the only variant implemented)
+#define USE_FAST_APPROXIMATE_EXP 1  // :64
 #endif
 #ifndef USE_UNIT_VECTOR_REJECTION_SAMPLING
-#define USE_UNIT_VECTOR_REJECTION_SAMPLING 1  // :65 (the only variant implemented)
+#define USE_UNIT_VECTOR_REJECTION_SAMPLING 1  // :65
 #endif
 #ifndef USE_RANDOM_JITTER_TEXTURE_SAMPLING
 #define USE_RANDOM_JITTER_TEXTURE_SAMPLING 1  // :66

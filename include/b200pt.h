@@ -83,7 +83,9 @@ enum {
 };
 
 /* ScreenBufferData packing, ..._optimization_v4.cpp:1285-1290 (screen) / :1321-1325 (file) */
-enum { B200PT_LDR_FILE_RGBA = 0, B200PT_LDR_SCREEN_BGRA = 1 };
+enum { B200PT_LDR_FILE_RGBA = 0, B200PT_LDR_SCREEN_BGRA = 1,
+       B200PT_LDR_EXACT_ACES = 2 /* OR into either packing: the exact ACES curve (USE_FAST_APPROXIMATE_ACES_TONEMAP 0,
+                                    ..._optimization_v4.cpp:172-175) instead of the fast one (:168-171) */ };
 
 /* mirrors struct texture, texture.h:6-12 (row-major RGB f32, row 0 = bottom after stbi's flip) */
 typedef struct b200pt_texture {
@@ -111,7 +113,15 @@ typedef struct b200pt_params {
     int32_t scheduler;              /* B200PT_SCHED_*: how paths are mapped to threads (results are identical) */
     int32_t disable_item_order;     /* 1: pull the work items in buffer order instead of scene-first / sky-last
                                        (A/B measurements; results are identical) */
-    int32_t reserved[3];
+    /* The reference's compile-time switches of global_preprocessor_flags.h:63-65, NON-default side; 0 keeps the checked-in
+     * defaults (all "fast").  OPT_V4 only (the other profiles' sources do not read them); each one selects the generic
+     * (table-driven) kernel, so expect the throughput of generic_scene_tables = 1. */
+    int32_t exact_exp;              /* 1: USE_FAST_APPROXIMATE_EXP 0 -- Beer-Lambert absorption through exp_ps instead of the
+                                       (1 + x/16.68)^16 approximation (..._optimization_v4.cpp:783-787) */
+    int32_t sincos_unit_vectors;    /* 1: USE_UNIT_VECTOR_REJECTION_SAMPLING 0 -- RandomUnitVector (2 draws, sin/cos) and exact
+                                       normalisations instead of the normalised cube sample (3 draws), :838-861 */
+    int32_t exact_aces_tonemap;     /* 1: USE_FAST_APPROXIMATE_ACES_TONEMAP 0 -- every tone map of this context (resolve_ldr,
+                                       present, OUTPUT_TO_SCREEN) uses the exact ACES curve, :172-175.  Any profile. */
 } b200pt_params;
 
 typedef struct b200pt_counters {

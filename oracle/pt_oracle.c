@@ -759,7 +759,10 @@ static v3 GetColorForRay_v4(const ctx_t* c, v3 rayPos, v3 rayDir, uint32_t* rng,
         const mat4_t* m = &s->mat[h.matIndex];
         if (h.fromInside) {
             v3 a = muls(neg3(m->refractionColor), h.dist);
-            throughput = mul3(throughput, V3(approx_exp1(a.x), approx_exp1(a.y), approx_exp1(a.z)));
+            if (c->p->v4_flags & 1) /* USE_FAST_APPROXIMATE_EXP 0: exp_ps, v4.cpp:786 */
+                throughput = mul3(throughput, V3(pm_expf(a.x), pm_expf(a.y), pm_expf(a.z)));
+            else
+                throughput = mul3(throughput, V3(approx_exp1(a.x), approx_exp1(a.y), approx_exp1(a.z)));
         }
         float specularChance = m->specularChance;
         float refractionChance = m->refractionChance;
@@ -789,15 +792,21 @@ static v3 GetColorForRay_v4(const ctx_t* c, v3 rayPos, v3 rayDir, uint32_t* rng,
         float doRefractionSign = doRefraction ? -1.f : 1.f;
         v3 newRayPos = fma3s(c_rayPosNormalNudge * doRefractionSign, h.normal, fma3s(h.dist, rayDir, rayPos));
 
-        v3 diffuseRayDir = fast_approx_normalize3(add3(h.normal, RandomUnitVectorRejectionSample(rng)));
+        const int sincos_uv = (c->p->v4_flags & 2) != 0; /* USE_UNIT_VECTOR_REJECTION_SAMPLING 0, v4.cpp:838-861 */
+        v3 diffuseRayDir = sincos_uv ? normalize3(add3(h.normal, RandomUnitVector(rng)))
+                                     : fast_approx_normalize3(add3(h.normal, RandomUnitVectorRejectionSample(rng)));
         v3 specularRayDir = fma3s(-(2.f * dot3(rayDir, h.normal)), h.normal, rayDir);
         float specularRoughnessSqrd = m->specularRoughness * m->specularRoughness;
         specularRayDir = fma3s(specularRoughnessSqrd, sub3(diffuseRayDir, specularRayDir), specularRayDir);
         float IOR = h.fromInside ? m->IOR : rcp_exact(m->IOR);
         float refractionRoughnessSquared = m->refractionRoughness * m->refractionRoughness;
         v3 refractionRayDir = rfrct(rayDir, h.normal, IOR);
-        v3 newRefractionDir = fast_approx_normalize3(sub3(RandomUnitVectorRejectionSample(rng), h.normal));
-        refractionRayDir = fma3s(refractionRoughnessSquared, sub3(newRefractionDir, refractionRayDir), refractionRayDir);
+        if (sincos_uv) {
+            refractionRayDir = normalize3(lerp3(refractionRayDir, normalize3(sub3(RandomUnitVector(rng), h.normal)), refractionRoughnessSquared));
+        } else {
+            v3 newRefractionDir = fast_approx_normalize3(sub3(RandomUnitVectorRejectionSample(rng), h.normal));
+            refractionRayDir = fma3s(refractionRoughnessSquared, sub3(newRefractionDir, refractionRayDir), refractionRayDir);
+        }
         v3 newRayDir = doSpecular ? specularRayDir : diffuseRayDir;
         if (doRefraction) newRayDir = refractionRayDir;
         newRayDir = normalize3(newRayDir);
@@ -1099,6 +1108,11 @@ static float aces1(float X)
     float rcpDenom = rcp_exact(FMA(X, FMA(cc, X, d), e));
     return saturate1((X * FMA(a, X, b)) * rcpDenom);
 }
+static float aces1_exact(float X) /* USE_FAST_APPROXIMATE_ACES_TONEMAP 0, v4.cpp:172-175 */
+{
+    const float a = 2.51f, b = 0.03f, cc = 2.43f, d = 0.59f, e = 0.14f;
+    return saturate1((X * (a * X + b)) / (X * (cc * X + d) + e));
+}
 static float srgb1(float v)
 {
     v = saturate1(v);
@@ -1114,11 +1128,11 @@ int oracle_resolve_ldr(const float* target, int W, int H, int ntx, int nty, uint
             float c[3] = {px[0], px[8], px[16]};
             uint32_t q[3];
             for (int k = 0; k < 3; k++) {
-                float v = srgb1(aces1(c[k] * 1.0f));
+                float v = srgb1((mode & 2) ? aces1_exact(c[k] * 1.0f) : aces1(c[k] * 1.0f));
                 v = saturate1(v) * 255.f;
                 q[k] = (uint32_t)to_epi32(v) & 0xFFu;
             }
-            out[(size_t)y * W + x] = (mode == 0) ? (0xFF000000u | (q[2] << 16) | (q[1] << 8) | q[0])
+            out[(size_t)y * W + x] = ((mode & 1) == 0) ? (0xFF000000u | (q[2] << 16) | (q[1] << 8) | q[0])
                                                  : ((q[0] << 16) | (q[1] << 8) | q[2]);
         }
     return 0;

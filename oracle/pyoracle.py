@@ -46,7 +46,9 @@ class OracleParams(ctypes.Structure):
         ("env_height", ctypes.c_int),
         ("scene_v4", ctypes.POINTER(OracleSceneV4)),
         ("scene_cornell", ctypes.POINTER(OracleSceneCornell)),
+        ("v4_flags", ctypes.c_int),
     ]
+V4_EXACT_EXP, V4_SINCOS_UNIT_VECTORS = 1, 2
 
 
 class OracleCounters(ctypes.Structure):
@@ -112,8 +114,9 @@ def make_scene_cornell(quads, spheres, materials):
     return sc, (q, s, m)
 
 
-def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=ENV_NONE, env_sampler=SAMPLER_POINT):
+def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=ENV_NONE, env_sampler=SAMPLER_POINT, v4_flags=0):
     p = OracleParams()
+    p.v4_flags = int(v4_flags)
     p.profile, p.width, p.height = profile, width, height
     p.num_tiles_x, p.num_tiles_y, p.num_bounces = ntx, nty, bounces
     p.env_kind, p.env_sampler = env_kind, env_sampler
@@ -127,7 +130,7 @@ def make_params(profile, width, height, ntx, nty, bounces, env=None, env_kind=EN
 
 
 def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, env=None, env_kind=ENV_NONE,
-           env_sampler=SAMPLER_POINT, target=None, nthreads=0, scene_v4=None, scene_cornell=None):
+           env_sampler=SAMPLER_POINT, target=None, nthreads=0, scene_v4=None, scene_cornell=None, v4_flags=0):
     """Returns (tile-major f32 buffer, counters dict).  scene_v4: result of make_scene_v4 (V4 profile);
     scene_cornell: result of make_scene_cornell (V2 / SIMT_TEXTURED profiles)."""
     p, keep = make_params(profile, width, height, ntx, nty, bounces, env, env_kind, env_sampler)
@@ -135,6 +138,7 @@ def render(profile, width, height, ntx, nty, bounces, nframes, first_frame=1, en
         p.scene_v4 = ctypes.pointer(scene_v4[0])
     if scene_cornell is not None:
         p.scene_cornell = ctypes.pointer(scene_cornell[0])
+    p.v4_flags = int(v4_flags)
     if target is None:
         target = np.zeros(width * height * 3, dtype=np.float32)
     else:

@@ -6,6 +6,8 @@
 #   * "const int c_numBounces = N;"  -> "int c_numBounces = N;"      (harness sets --bounces)
 #   * "static f32 iFrame = 0.f;"     -> "f32 iFrame = 0.f;"          (harness sets --start-frame)
 #   * NUM_THREADS                    -> oracle_num_threads            (harness sets --threads)
+#   * v4 only: USE_FAST_APPROXIMATE_EXP / USE_UNIT_VECTOR_REJECTION_SAMPLING / USE_FAST_APPROXIMATE_ACES_TONEMAP are renamed
+#     ORACLE_<name> the same way (checked-in value 1 unless a variant says otherwise)
 #   * v3_redo only: "#define SCENE 1" -> "#ifndef SCENE / #define SCENE 1 / #endif" so that -DSCENE=0 selects the
 #     renderer's other checked-in scene (demofox_path_tracing_v3_redo.cpp:379,392-479,530-580)
 #   * v4 only: the compile-time switches of global_preprocessor_flags.h:56-66 that pick the env
@@ -23,7 +25,9 @@ if [ ! -f "$REF/demofox_path_tracing_v2.cpp" ]; then
     exit 0
 fi
 
+# the three shading / tone-map switches keep their checked-in value (1) unless a variant overrides them
 BASE="-std=c++17 -O2 -mavx2 -mfma -fno-operator-names -fpermissive -w -I$HERE/stubs -I$HERE -I$HERE/.. -I$REF"
+DEFAULT_SWITCHES="-DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1"
 flags_for_mode() { if [ "$1" = exact ]; then echo "-DORACLE_EXACT=1 -ffp-contract=off"; else echo "-DORACLE_EXACT=0"; fi; }
 
 PATCH=(-E
@@ -33,7 +37,10 @@ PATCH=(-E
   -e 's/^#define SCENE 1$/#ifndef SCENE\n#define SCENE 1\n#endif/'
   -e 's/^#if USE_ENV_CUBEMAP/#if ORACLE_USE_ENV_CUBEMAP/'
   -e 's/^#if USE_RANDOM_JITTER_TEXTURE_SAMPLING/#if ORACLE_USE_RANDOM_JITTER_TEXTURE_SAMPLING/'
-  -e 's/^#if OUTPUT_TO_SCREEN/#if ORACLE_OUTPUT_TO_SCREEN/')
+  -e 's/^#if OUTPUT_TO_SCREEN/#if ORACLE_OUTPUT_TO_SCREEN/'
+  -e 's/^#if USE_FAST_APPROXIMATE_EXP/#if ORACLE_USE_FAST_APPROXIMATE_EXP/'
+  -e 's/^#if USE_UNIT_VECTOR_REJECTION_SAMPLING/#if ORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING/'
+  -e 's/^#if USE_FAST_APPROXIMATE_ACES_TONEMAP/#if ORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP/')
 
 compile_stream() { # $1=source file in $REF, $2=object, rest=flags
     local src="$1" obj="$2"; shift 2
@@ -44,7 +51,9 @@ build_variant() { # $1=binary name $2=variant id $3=variant source $4=mode, rest
     local name="$1" vid="$2" src="$3" mode="$4"; shift 4
     local mf; mf="$(flags_for_mode "$mode")"
     local o="$OUT/obj/$name"
-    compile_stream "$src" "$o.variant.o" $mf "$@"
+    local sw="$DEFAULT_SWITCHES"
+    case " $* " in *ORACLE_USE_FAST_APPROXIMATE_EXP=*|*ORACLE_USE_UNIT_VECTOR*|*ORACLE_USE_FAST_APPROXIMATE_ACES*) sw="";; esac
+    compile_stream "$src" "$o.variant.o" $mf $sw "$@"
     compile_stream texture.cpp "$o.texture.o" $mf "$@"
     compile_stream work_queue.cpp "$o.wq.o" $mf "$@"
     $CXX $BASE $mf -DORACLE_VARIANT="$vid" -include "$HERE/shim.h" -c "$HERE/harness.cpp" -o "$o.harness.o"
@@ -66,6 +75,13 @@ for mode in exact asis; do
     build_variant "ref_v3redo_scene0_$mode" 4 demofox_path_tracing_v3_redo.cpp "$mode" -DSCENE=0 &
     for j in $(jobs -p); do wait "$j"; done
 done
+# the non-default shading / tone-map switches of global_preprocessor_flags.h:63-65 (exact mode only: parity anchors)
+build_variant ref_v4_equirect_random_expexact_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=0 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 &
+build_variant ref_v4_equirect_random_sincos_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=0 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 &
+build_variant ref_v4_equirect_random_allexact_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=0 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=0 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=0 &
 build_variant ref_v4_equirect_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_BILIN &
 build_variant ref_v4_cubemap_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_CUBE_BILIN &
 # the reference's asset loader (stb_image / stb_image_write, vendored in the reference tree)

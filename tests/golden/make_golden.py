@@ -5,7 +5,8 @@ Runs the binaries that oracle/ref_build/build_ref.sh compiles in place from /roo
 fixtures pin oracle/pt_oracle.c (tests/test_oracle_golden.py) and the CUDA path
 (tests/test_gpu_parity.py) on machines where /root/reference does not exist.
 
-    python tests/golden/make_golden.py        # needs /root/reference (this container)
+    python tests/golden/make_golden.py                   # needs /root/reference (this container)
+    python tests/golden/make_golden.py --only NAME ...   # (re)generate the named fixtures only, keep the rest of the index
 
 Env textures are the deterministic synthetic ones of oracle.pyoracle.synthetic_env, regenerated
 by the tests from (width, height), so no texture data is stored.
@@ -40,11 +41,27 @@ CASES = [
     ("v4_b16", "ref_v4_equirect_random_exact", po.PROFILE_V4, po.ENV_EQUIRECT, po.SAMPLER_RANDOM,
      (128, 64), 64, 40, 2, 5, 16, 4),
 ]
+# the NON-default sides of global_preprocessor_flags.h:63-65 (build_ref.sh compiles one binary per combination):
+# name, ref binary, oracle v4_flags (pyoracle.V4_EXACT_EXP | V4_SINCOS_UNIT_VECTORS)
+FLAG_CASES = [
+    ("v4_exact_exp", "ref_v4_equirect_random_expexact_exact", po.V4_EXACT_EXP),
+    ("v4_sincos_unit_vectors", "ref_v4_equirect_random_sincos_exact", po.V4_SINCOS_UNIT_VECTORS),
+    ("v4_all_exact", "ref_v4_equirect_random_allexact_exact", po.V4_EXACT_EXP | po.V4_SINCOS_UNIT_VECTORS),
+]
 
 
 def main():
+    only = sys.argv[sys.argv.index("--only") + 1:] if "--only" in sys.argv else None
     index = []
-    for (name, binary, profile, ek, es, envshape, W, H, ntx, nty, bounces, frames) in CASES:
+    if only is not None:
+        with open(os.path.join(HERE, "index.json")) as f:
+            index = [e for e in json.load(f) if e["name"] not in only]
+    cases = [c + (0,) for c in CASES]
+    cases += [(name, binary, po.PROFILE_V4, po.ENV_EQUIRECT, po.SAMPLER_RANDOM, (128, 64), 128, 72, 4, 6, 8, 6, flags)
+              for (name, binary, flags) in FLAG_CASES]
+    for (name, binary, profile, ek, es, envshape, W, H, ntx, nty, bounces, frames, v4_flags) in cases:
+        if only is not None and name not in only:
+            continue
         env = po.synthetic_env(*envshape) if envshape else None
         res = po.run_ref(binary, W, H, ntx, nty, frames, bounces=bounces, env=env)
         buf = res["buffer"]
@@ -54,15 +71,18 @@ def main():
         np.savez_compressed(os.path.join(HERE, name + ".npz"), buffer=buf, continued=cont)
         index.append(dict(name=name, binary=binary, profile=profile, env_kind=ek, env_sampler=es,
                           env_shape=list(envshape) if envshape else None, width=W, height=H, ntx=ntx, nty=nty,
-                          bounces=bounces, frames=frames, continued_frames=2))
+                          bounces=bounces, frames=frames, continued_frames=2, v4_flags=v4_flags))
         print(name, "mean", float(buf.mean()))
-    # LDR golden from the reference's CopyOutputToFile (single queue participant: deterministic)
-    name, binary = "v4_ldr", "ref_v4_equirect_random_exact"
+    # LDR goldens from the reference's CopyOutputToFile (single queue participant: deterministic); the second one is the
+    # build with USE_FAST_APPROXIMATE_ACES_TONEMAP 0 (and the other two switches off as well)
     env = po.synthetic_env(128, 64)
-    res = po.run_ref(binary, 128, 72, 4, 6, 6, bounces=8, env=env, threads=1, ldr=True)
-    np.savez_compressed(os.path.join(HERE, name + ".npz"), buffer=res["buffer"], ldr=res["ldr"])
-    index.append(dict(name=name, binary=binary, kind="ldr", width=128, height=72, ntx=4, nty=6, bounces=8, frames=6,
-                      env_shape=[128, 64]))
+    for name, binary, exact_aces in (("v4_ldr", "ref_v4_equirect_random_exact", 0), ("v4_ldr_exact_aces", "ref_v4_equirect_random_allexact_exact", 1)):
+        if only is not None and name not in only:
+            continue
+        res = po.run_ref(binary, 128, 72, 4, 6, 6, bounces=8, env=env, threads=1, ldr=True)
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), buffer=res["buffer"], ldr=res["ldr"])
+        index.append(dict(name=name, binary=binary, kind="ldr", width=128, height=72, ntx=4, nty=6, bounces=8, frames=6,
+                          env_shape=[128, 64], exact_aces=exact_aces))
     with open(os.path.join(HERE, "index.json"), "w") as f:
         json.dump(index, f, indent=1)
 

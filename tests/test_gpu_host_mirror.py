@@ -86,6 +86,28 @@ def test_render_offline_v4_equirect(oracle, io, tmp_path):
     assert np.array_equal(g, o)
 
 
+def read_bmp24(path, w, h):
+    """rows of the 24-bit BMP the CLI writes (bottom row first, B G R bytes) -> (h, w) of R | G<<8 | B<<16, top row first"""
+    b = np.frombuffer(open(path, "rb").read(), np.uint8)
+    stride = (w * 3 + 3) & ~3
+    rows = b[54:54 + stride * h].reshape(h, stride)[::-1, :w * 3].reshape(h, w, 3).astype(np.uint32)
+    return rows[:, :, 2] | (rows[:, :, 1] << 8) | (rows[:, :, 0] << 16)
+
+
+def test_render_offline_v4_non_default_switches(oracle, io, tmp_path):
+    """--exact-exp / --sincos-unit-vectors / --exact-aces = USE_FAST_APPROXIMATE_EXP, USE_UNIT_VECTOR_REJECTION_SAMPLING,
+    USE_FAST_APPROXIMATE_ACES_TONEMAP set to 0 (global_preprocessor_flags.h:63-65): f32 dump and the written .bmp"""
+    path, tex = make_equirect(tmp_path, oracle, io)
+    for args, flags, aces in ((["--exact-exp"], oracle.V4_EXACT_EXP, 0), (["--sincos-unit-vectors"], oracle.V4_SINCOS_UNIT_VECTORS, 0),
+                              (["--exact-exp", "--sincos-unit-vectors", "--exact-aces"], 3, 2)):
+        g, _ = run_cli(tmp_path, "--variant", "v4", "--env", path, *args, name="sw")
+        o, _ = oracle.render(oracle.PROFILE_V4, W, H, NTX, NTY, 8, FRAMES + 2, env=tex, env_kind=oracle.ENV_EQUIRECT,
+                             env_sampler=oracle.SAMPLER_RANDOM, v4_flags=flags)
+        assert np.array_equal(g, o)
+        ldr = oracle.resolve_ldr(o, W, H, NTX, NTY, mode=aces).reshape(H, W) & 0xFFFFFF
+        assert np.array_equal(read_bmp24(tmp_path / "sw.bmp", W, H), ldr)
+
+
 def test_render_offline_v4_cubemap(oracle, io, tmp_path):
     paths, atlas = make_cubemap(tmp_path, oracle, io)
     for extra, sampler in (([], oracle.SAMPLER_RANDOM), (["--bilinear"], oracle.SAMPLER_BILINEAR)):

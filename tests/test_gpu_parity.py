@@ -30,7 +30,9 @@ def test_parity_mode_reproduces_reference_golden(oracle, case):
     """GPU vs buffers produced by the reference's own code (tests/golden)."""
     g = load_golden(case["name"])
     env = oracle.synthetic_env(*case["env_shape"]) if case["env_shape"] else None
-    with make_renderer(case["profile"], case["bounces"], case["env_kind"], case["env_sampler"]) as r:
+    flags = case.get("v4_flags", 0)  # the non-default sides of global_preprocessor_flags.h:64-65
+    kw = dict(exact_exp=bool(flags & oracle.V4_EXACT_EXP), sincos_unit_vectors=bool(flags & oracle.V4_SINCOS_UNIT_VECTORS)) if flags else {}
+    with make_renderer(case["profile"], case["bounces"], case["env_kind"], case["env_sampler"], **kw) as r:
         if env is not None:
             r.set_env(env)
         r.resize(case["width"], case["height"], case["ntx"], case["nty"])
@@ -179,6 +181,90 @@ def test_ldr_resolve_bit_exact(oracle):
         r.render_host(buf, 128, 72, 4, 6, 6, screen=scr)
         assert np.array_equal(buf, g["buffer"])
         assert np.array_equal(scr, oracle.resolve_ldr(buf, 128, 72, 4, 6, mode=1))
+
+
+SWITCH_CASES = [(1, 0, api.ENV_EQUIRECT, api.SAMPLER_RANDOM), (0, 1, api.ENV_CUBEMAP, api.SAMPLER_BILINEAR),
+                (1, 1, api.ENV_CUBEMAP, api.SAMPLER_RANDOM), (1, 1, api.ENV_NONE, api.SAMPLER_RANDOM)]
+
+
+@pytest.mark.parametrize("exact_exp,sincos,ek,es", SWITCH_CASES)
+@pytest.mark.parametrize("sched", [api.SCHED_LANE, api.SCHED_SORTED])
+def test_non_default_switches_bit_exact_vs_oracle(oracle, exact_exp, sincos, ek, es, sched):
+    """USE_FAST_APPROXIMATE_EXP 0 / USE_UNIT_VECTOR_REJECTION_SAMPLING 0 (global_preprocessor_flags.h:64-65): buffer, RNG
+    states (2 + 2 draws per bounce instead of 3 + 3) and counters against the oracle, which is pinned on reference builds
+    with those switches flipped (tests/golden v4_exact_exp, v4_sincos_unit_vectors, v4_all_exact)"""
+    import ctypes
+    W, H, ntx, nty, frames, bounces = 256, 192, 4, 6, 10, 8
+    env = None if ek == api.ENV_NONE else oracle.synthetic_env(*((64, 384) if ek == api.ENV_CUBEMAP else (256, 128)))
+    flags = (oracle.V4_EXACT_EXP if exact_exp else 0) | (oracle.V4_SINCOS_UNIT_VECTORS if sincos else 0)
+    o, oc = oracle.render(oracle.PROFILE_V4, W, H, ntx, nty, bounces, frames, env=env, env_kind=ek, env_sampler=es, v4_flags=flags)
+    with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=bounces, env_kind=ek, env_sampler=es, scheduler=sched,
+                      exact_exp=exact_exp, sincos_unit_vectors=sincos) as r:
+        if env is not None:
+            r.set_env(env)
+        r.resize(W, H, ntx, nty)
+        r.render_frames(4)
+        r.render_frames(frames - 4)
+        g = r.download_target()
+        assert np.array_equal(g, o), "max abs %g rmse %g" % stats(g, o)
+        c = r.counters()
+        assert (c["paths"], c["segments"], c["escapes"]) == (oc["paths"], oc["segments"], oc["escapes"])
+        rs = r.rng_state()
+        p, keep = oracle.make_params(oracle.PROFILE_V4, W, H, ntx, nty, bounces, env, ek, es, v4_flags=flags)
+        rng = np.random.default_rng(11)
+        for _ in range(200):
+            x, y = int(rng.integers(W)), int(rng.integers(H))
+            assert int(rs[y, x]) == oracle.lib().oracle_final_rng_state(ctypes.byref(p), x, y, frames)
+
+
+def test_non_default_switches_are_v4_only_and_fast_math_stays_close(oracle):
+    for prof in (api.PROFILE_V2, api.PROFILE_SIMT_TEXTURED, api.PROFILE_V3_REDO):
+        with pytest.raises(api.B200PTError):
+            api.Renderer(profile=prof, exact_exp=True)
+        with pytest.raises(api.B200PTError):
+            api.Renderer(profile=prof, sincos_unit_vectors=True)
+    # fast math with the switches on: same image within Monte-Carlo noise of the parity render (both 64 spp)
+    W, H, ntx, nty, frames = 256, 192, 4, 6, 64
+    env = oracle.synthetic_env(256, 128)
+    imgs = []
+    for mm in (api.MATH_PARITY, api.MATH_FAST):
+        with api.Renderer(profile=api.PROFILE_OPT_V4, math_mode=mm, exact_exp=True, sincos_unit_vectors=True) as r:
+            r.set_env(env)
+            r.resize(W, H, ntx, nty)
+            r.render_frames(frames)
+            imgs.append(r.download_target().astype(np.float64))
+    assert np.isfinite(imgs[1]).all()
+    assert abs(imgs[0].mean() - imgs[1].mean()) < 0.01 * imgs[0].mean()
+
+
+def test_exact_aces_tonemap_bit_exact(oracle):
+    """USE_FAST_APPROXIMATE_ACES_TONEMAP 0 (global_preprocessor_flags.h:63): resolve, fused screen output and present"""
+    g = load_golden("v4_ldr_exact_aces")
+    W, H, ntx, nty = 128, 72, 4, 6
+    with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=8, output_to_screen=True, exact_exp=True, sincos_unit_vectors=True,
+                      exact_aces_tonemap=True) as r:
+        r.set_env(oracle.synthetic_env(128, 64))
+        r.resize(W, H, ntx, nty)
+        r.upload_target(g["buffer"])
+        assert np.array_equal(r.resolve_ldr(api.LDR_FILE_RGBA), g["ldr"])  # the reference build's CopyOutputToFile
+        assert np.array_equal(r.resolve_ldr(api.LDR_SCREEN_BGRA), oracle.resolve_ldr(g["buffer"], W, H, ntx, nty, mode=3))
+        buf = np.zeros(W * H * 3, dtype=np.float32)
+        scr = np.zeros((H, W), dtype=np.uint32)
+        r.frame_counter = 0
+        r.render_host(buf, W, H, ntx, nty, 6, screen=scr)  # fused tone map in the render kernel's tail
+        assert np.array_equal(buf, g["buffer"])
+        assert np.array_equal(scr, oracle.resolve_ldr(buf, W, H, ntx, nty, mode=3))
+    # per call (mode | LDR_EXACT_ACES) on a context with the default curve, on values where the two curves differ at 8 bits
+    rng = np.random.default_rng(1)
+    W2, H2 = 4096, 64
+    vals = (rng.random(W2 * H2 * 3, dtype=np.float32) ** 3 * 4).astype(np.float32)
+    with api.Renderer(profile=api.PROFILE_V2) as r:
+        r.resize(W2, H2, 1, 1)
+        r.upload_target(vals)
+        fast, exact = r.resolve_ldr(api.LDR_FILE_RGBA), r.resolve_ldr(api.LDR_FILE_RGBA | api.LDR_EXACT_ACES)
+        assert np.array_equal(fast, oracle.resolve_ldr(vals, W2, H2, 1, 1, mode=0))
+        assert np.array_equal(exact, oracle.resolve_ldr(vals, W2, H2, 1, 1, mode=2))
+        assert not np.array_equal(fast, exact)
 
 
 def test_sum_mode_matches_running_average(oracle):

@@ -45,6 +45,25 @@ def test_v4(oracle, name, kind, sampler, envshape):
 
 
 @needs_ref
+@pytest.mark.parametrize("name,flags", [("ref_v4_equirect_random_expexact_exact", po.V4_EXACT_EXP),
+                                        ("ref_v4_equirect_random_sincos_exact", po.V4_SINCOS_UNIT_VECTORS),
+                                        ("ref_v4_equirect_random_allexact_exact", po.V4_EXACT_EXP | po.V4_SINCOS_UNIT_VECTORS)])
+def test_v4_non_default_switches(oracle, name, flags):
+    """reference builds with USE_FAST_APPROXIMATE_EXP / USE_UNIT_VECTOR_REJECTION_SAMPLING (/ ..._ACES_TONEMAP) set to 0
+    (global_preprocessor_flags.h:63-65; oracle/ref_build/build_ref.sh) against the oracle's v4_flags"""
+    if po.ref_binary(name) is None:
+        pytest.skip(name + " not built")
+    W, H = 320, 180
+    env = po.synthetic_env(256, 128)
+    o, _ = oracle.render(po.PROFILE_V4, W, H, 10, 15, 8, 4, env=env, env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_RANDOM, v4_flags=flags)
+    r = po.run_ref(name, W, H, 10, 15, 4, bounces=8, env=env)["buffer"]
+    assert np.array_equal(o, r)
+    if flags == 3:  # that build's CopyOutputToFile uses the exact ACES curve
+        res = po.run_ref(name, W, H, 10, 15, 4, bounces=8, env=env, threads=1, ldr=True)
+        assert np.array_equal(res["ldr"], oracle.resolve_ldr(res["buffer"], W, H, 10, 15, mode=2))
+
+
+@needs_ref
 @pytest.mark.parametrize("bounces,frames,tiles", [(8, 4, (2, 4)), (16, 2, (4, 2))])
 def test_v3_redo(oracle, bounces, frames, tiles):
     W, H = 256, 144
