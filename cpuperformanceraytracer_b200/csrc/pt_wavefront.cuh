@@ -67,6 +67,7 @@ pt_render_sorted_kernel(const __grid_constant__ RenderParams p, const __grid_con
         S.smat[i] = obj < kObjects ? reinterpret_cast<const float*>(&scene.mat[obj])[field] : 0.f;
     }
     if constexpr (PROFILE != kProfileV4) build_legacy_variants(S.trace, scene);
+    else if constexpr (!STATIC) build_v4_shared(S.trace, scene);
     if (threadIdx.x < 16) (&S.cls[0][0])[threadIdx.x] = 0;
     __syncthreads();
 
