@@ -18,7 +18,8 @@ MATH_PARITY, MATH_FAST = 0, 1
 ENV_NONE, ENV_EQUIRECT, ENV_CUBEMAP = 0, 1, 2
 SAMPLER_POINT, SAMPLER_BILINEAR, SAMPLER_RANDOM = 0, 1, 2
 ACCUM_RUNNING_AVERAGE, ACCUM_SUM = 0, 1
-LDR_FILE_RGBA, LDR_SCREEN_BGRA, LDR_EXACT_ACES = 0, 1, 2
+LDR_FILE_RGBA, LDR_SCREEN_BGRA, LDR_EXACT_ACES, LDR_EXACT_GAMMA = 0, 1, 2, 4
+TONEMAP_EXACT_ACES, TONEMAP_EXACT_GAMMA = 1, 2
 SCHED_DEFAULT, SCHED_LANE, SCHED_SORTED = 0, 1, 2
 
 # every symbol include/b200pt.h declares (tests/test_abi.py checks the library exports them all)
@@ -37,7 +38,7 @@ ABI_SYMBOLS = [
 ]
 SHARD_SPP, SHARD_TILES = 0, 1
 COMBINE_NCCL, COMBINE_PEER, COMBINE_FUSED = 0, 1, 2
-FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP, FN_SQRT, FN_RCP, FN_DIV, FN_EQUIRECT_TEXEL = 0, 1, 2, 3, 4, 5, 6, 7, 8
+FN_SIN, FN_COS, FN_ATAN2, FN_ASIN, FN_EXP, FN_SQRT, FN_RCP, FN_DIV, FN_EQUIRECT_TEXEL, FN_POW = 0, 1, 2, 3, 4, 5, 6, 7, 8, 9
 
 
 class Texture(ctypes.Structure):
@@ -52,7 +53,7 @@ class Params(ctypes.Structure):
                 ("env_sampler", ctypes.c_int32), ("accum_mode", ctypes.c_int32), ("output_to_screen", ctypes.c_int32),
                 ("disable_camera_culling", ctypes.c_int32), ("generic_scene_tables", ctypes.c_int32),
                 ("scheduler", ctypes.c_int32), ("disable_item_order", ctypes.c_int32), ("exact_exp", ctypes.c_int32),
-                ("sincos_unit_vectors", ctypes.c_int32), ("exact_aces_tonemap", ctypes.c_int32)]
+                ("sincos_unit_vectors", ctypes.c_int32), ("exact_tonemap", ctypes.c_int32)]
 
 
 class Counters(ctypes.Structure):
@@ -163,7 +164,7 @@ class Renderer:
     def __init__(self, profile=PROFILE_V2, math_mode=MATH_PARITY, num_bounces=-1, device=0, env_kind=None,
                  env_sampler=None, accum_mode=ACCUM_RUNNING_AVERAGE, output_to_screen=False,
                  disable_camera_culling=False, generic_scene_tables=False, scheduler=SCHED_DEFAULT, disable_item_order=False,
-                 exact_exp=False, sincos_unit_vectors=False, exact_aces_tonemap=False):
+                 exact_exp=False, sincos_unit_vectors=False, exact_aces_tonemap=False, exact_gamma=False):
         self._lib = load_library()
         self._ctx = ctypes.c_void_p()
         p = default_params(profile)
@@ -175,7 +176,7 @@ class Renderer:
         p.disable_item_order = int(bool(disable_item_order))
         # global_preprocessor_flags.h:63-65, non-default side (0 = the reference's checked-in "fast" variants)
         p.exact_exp, p.sincos_unit_vectors = int(bool(exact_exp)), int(bool(sincos_unit_vectors))
-        p.exact_aces_tonemap = int(bool(exact_aces_tonemap))
+        p.exact_tonemap = (TONEMAP_EXACT_ACES if exact_aces_tonemap else 0) | (TONEMAP_EXACT_GAMMA if exact_gamma else 0)
         if env_kind is not None:
             p.env_kind = env_kind
         if env_sampler is not None:
@@ -405,13 +406,13 @@ class Group:
 
     def __init__(self, devices, sharding=SHARD_SPP, combine=COMBINE_NCCL, profile=PROFILE_V2, math_mode=MATH_PARITY,
                  num_bounces=-1, env_kind=None, env_sampler=None, output_to_screen=False, scheduler=SCHED_DEFAULT,
-                 exact_exp=False, sincos_unit_vectors=False, exact_aces_tonemap=False):
+                 exact_exp=False, sincos_unit_vectors=False, exact_aces_tonemap=False, exact_gamma=False):
         self._lib = load_library()
         self._g = ctypes.c_void_p()
         p = default_params(profile)
         p.math_mode, p.num_bounces = math_mode, num_bounces
         p.exact_exp, p.sincos_unit_vectors = int(bool(exact_exp)), int(bool(sincos_unit_vectors))
-        p.exact_aces_tonemap = int(bool(exact_aces_tonemap))
+        p.exact_tonemap = (TONEMAP_EXACT_ACES if exact_aces_tonemap else 0) | (TONEMAP_EXACT_GAMMA if exact_gamma else 0)
         p.scheduler = int(scheduler)
         p.output_to_screen = int(bool(output_to_screen))
         if env_kind is not None:

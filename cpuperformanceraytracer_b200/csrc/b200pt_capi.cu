@@ -203,6 +203,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     if (params->profile < B200PT_PROFILE_V2 || params->profile > B200PT_PROFILE_V3_REDO_SCENE0) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->math_mode != B200PT_MATH_PARITY && params->math_mode != B200PT_MATH_FAST) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->accum_mode != B200PT_ACCUM_RUNNING_AVERAGE && params->accum_mode != B200PT_ACCUM_SUM) return B200PT_ERR_INVALID_ARGUMENT;
+    if (params->exact_tonemap & ~(B200PT_TONEMAP_EXACT_ACES | B200PT_TONEMAP_EXACT_GAMMA)) return B200PT_ERR_INVALID_ARGUMENT;
     // the reference reads USE_FAST_APPROXIMATE_EXP / USE_UNIT_VECTOR_REJECTION_SAMPLING in the v4 source only
     if (params->profile != B200PT_PROFILE_OPT_V4 && (params->exact_exp || params->sincos_unit_vectors)) return B200PT_ERR_INVALID_ARGUMENT;
     if (params->profile == B200PT_PROFILE_OPT_V4) {
@@ -516,8 +517,11 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     RenderParams rp{};
     rp.target = c->d_target;
     rp.rng_out = c->d_rng;
-    rp.screen = screen;
-    rp.screen_mode = B200PT_LDR_SCREEN_BGRA | (c->params.exact_aces_tonemap ? B200PT_LDR_EXACT_ACES : 0);
+    // the pow() gamma is binary64 work that stays out of the render kernels: they skip their fused tone map and the resolve
+    // kernel follows on the same stream (every other tone map is fused; B200PT_LDR_EXACT_* = B200PT_TONEMAP_EXACT_* << 1)
+    const bool resolve_after = screen && (c->params.exact_tonemap & B200PT_TONEMAP_EXACT_GAMMA);
+    rp.screen = resolve_after ? nullptr : screen;
+    rp.screen_mode = B200PT_LDR_SCREEN_BGRA | ((c->params.exact_tonemap & B200PT_TONEMAP_EXACT_ACES) << 1);
     rp.v4_flags = (c->params.exact_exp ? 1 : 0) | (c->params.sincos_unit_vectors ? 2 : 0);
     rp.work_counter = c->d_work_counter;
     rp.counters = c->d_counters;
@@ -606,6 +610,11 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
         e = (c->params.math_mode == B200PT_MATH_PARITY) ? launch_render_parity(lc, rp, c->scenes, c->stream)
                                                         : launch_render_fast(lc, rp, c->scenes, c->stream);
     CUDA_TRY(c, e);
+    if (resolve_after) {
+        CUDA_TRY(c, launch_resolve_ldr(c->d_target, screen, c->width, c->height, c->tile_w, c->tile_h, c->ntx,
+                                       B200PT_LDR_SCREEN_BGRA | (c->params.exact_tonemap << 1), c->stream));
+        c->launches++;
+    }
     CUDA_TRY(c, cudaEventRecord(c->ev1[ts], c->stream));
     c->timing_pending[ts] = true;
     c->launches++;
@@ -714,9 +723,9 @@ int b200pt_render_host(b200pt_context* c, float* BufferOut, int32_t W, int32_t H
 
 int b200pt_resolve_ldr(b200pt_context* c, uint32_t* host_dst, int32_t mode, int32_t bump_frame_counter)
 {
-    if (!c || !host_dst || (mode & ~(B200PT_LDR_SCREEN_BGRA | B200PT_LDR_EXACT_ACES))) return B200PT_ERR_INVALID_ARGUMENT;
+    if (!c || !host_dst || (mode & ~(B200PT_LDR_SCREEN_BGRA | B200PT_LDR_EXACT_ACES | B200PT_LDR_EXACT_GAMMA))) return B200PT_ERR_INVALID_ARGUMENT;
     if (!c->d_target) return fail(c, B200PT_ERR_NOT_READY, "resize first");
-    if (c->params.exact_aces_tonemap) mode |= B200PT_LDR_EXACT_ACES;
+    mode |= c->params.exact_tonemap << 1;
     DeviceGuard guard(c->device);
     CUDA_TRY(c, guard.status);
     CUDA_TRY(c, cudaStreamSynchronize(c->copy_stream));  // the present ring may still be reading slot 0
@@ -945,7 +954,8 @@ int b200pt_download_rng_state(b200pt_context* c, uint32_t* host_dst)
 
 int b200pt_eval_portable(b200pt_context* c, int fn, const float* a, const float* b, float* out, size_t n)
 {
-    if (!c || !a || !out || fn < B200PT_FN_SIN || fn > B200PT_FN_EXP || (fn == B200PT_FN_ATAN2 && !b))
+    const bool two = fn == B200PT_FN_ATAN2 || fn == B200PT_FN_POW;
+    if (!c || !a || !out || ((fn < B200PT_FN_SIN || fn > B200PT_FN_EXP) && fn != B200PT_FN_POW) || (two && !b))
         return B200PT_ERR_INVALID_ARGUMENT;
     if (n == 0) return B200PT_OK;
     DeviceGuard guard(c->device);
@@ -953,7 +963,7 @@ int b200pt_eval_portable(b200pt_context* c, int fn, const float* a, const float*
     float *da = nullptr, *db = nullptr, *dout = nullptr;
     cudaError_t e = cudaMalloc(&da, n * sizeof(float));
     if (e == cudaSuccess) e = cudaMalloc(&dout, n * sizeof(float));
-    if (e == cudaSuccess && fn == B200PT_FN_ATAN2) e = cudaMalloc(&db, n * sizeof(float));
+    if (e == cudaSuccess && two) e = cudaMalloc(&db, n * sizeof(float));
     if (e == cudaSuccess) e = cudaMemcpyAsync(da, a, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess && db) e = cudaMemcpyAsync(db, b, n * sizeof(float), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = launch_eval_portable(fn, da, db, dout, n, c->stream);

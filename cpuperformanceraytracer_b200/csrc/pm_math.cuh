@@ -268,6 +268,7 @@ __device__ __forceinline__ float asinf_portable(float v)
 
 // exp of a binary32 argument (v3_redo absorption): k = rint(x / ln 2), two-part reduction, degree-13
 // Taylor polynomial, scaling through the exponent field, one rounding to binary32
+__device__ __forceinline__ double exp_core(double x);
 __device__ __forceinline__ float expf_portable(float a)
 {
     if (a == 0.f) return 1.0f;  // what the evaluation below gives; the built-in refraction colour has a zero channel
@@ -275,6 +276,11 @@ __device__ __forceinline__ float expf_portable(float a)
     if (x != x) return __int_as_float(0x7fc00000);
     if (x > 89.0) return __int_as_float(0x7f800000);
     if (x < -104.0) return 0.0f;
+    return __double2float_rn(exp_core(x));
+}
+// exp of a binary64 argument in [-104, 89], not yet rounded to binary32
+__device__ __forceinline__ double exp_core(double x)
+{
     const double LOG2E = 1.44269504088896338700e+00;
     const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
     double kd = rint(__dmul_rn(x, LOG2E));
@@ -295,7 +301,50 @@ __device__ __forceinline__ float expf_portable(float a)
     p = __fma_rn(r, p, 1.0);
     p = __fma_rn(r, p, 1.0);
     const double scale = __longlong_as_double((long long)((long long)kd + 1023) << 52);
-    return __double2float_rn(__dmul_rn(p, scale));
+    return __dmul_rn(p, scale);
+}
+
+// pow(x, y) for x >= 0 (the non-fast gamma: pow_ps(rgb, 1/2.4), v4.cpp:185) = oracle/portable_math.h's pm_powf, operation for
+// operation: exp(y log x) in binary64 -- x = 2^e m, m in [sqrt(1/2), sqrt(2)], log m = 2 s (1 + z/3 + ... + z^10/21) with
+// s = (m - 1) / (m + 1), z = s^2 -- rounded once to binary32
+__device__ __forceinline__ float powf_portable(float xf, float yf)
+{
+    const double x = (double)xf, y = (double)yf;
+    const float nan = __int_as_float(0x7fc00000), inf = __int_as_float(0x7f800000);
+    if (y == 0.0 || x == 1.0) return 1.0f;
+    if (x != x || y != y || x < 0.0) return nan;
+    if (x == 0.0) return y > 0.0 ? 0.0f : inf;
+    if (x == (double)inf) return y > 0.0 ? inf : 0.0f;
+    if (y == (double)inf) return x < 1.0 ? 0.0f : inf;
+    if (y == -(double)inf) return x < 1.0 ? inf : 0.0f;
+    long long u = __double_as_longlong(x);
+    long long e = ((u >> 52) & 0x7ff) - 1023;
+    double m = __longlong_as_double((u & 0x000fffffffffffffll) | 0x3ff0000000000000ll);
+    if (m > 1.41421356237309514547) {
+        m = __dmul_rn(m, 0.5);
+        e += 1;
+    }
+    const double s = __ddiv_rn(__dadd_rn(m, -1.0), __dadd_rn(m, 1.0));
+    const double z = __dmul_rn(s, s);
+    double p = 1.0 / 21.0;
+    p = __fma_rn(z, p, 1.0 / 19.0);
+    p = __fma_rn(z, p, 1.0 / 17.0);
+    p = __fma_rn(z, p, 1.0 / 15.0);
+    p = __fma_rn(z, p, 1.0 / 13.0);
+    p = __fma_rn(z, p, 1.0 / 11.0);
+    p = __fma_rn(z, p, 1.0 / 9.0);
+    p = __fma_rn(z, p, 1.0 / 7.0);
+    p = __fma_rn(z, p, 1.0 / 5.0);
+    p = __fma_rn(z, p, 1.0 / 3.0);
+    p = __fma_rn(z, p, 1.0);
+    const double logm = __dmul_rn(__dadd_rn(s, s), p);
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double ed = (double)e;
+    const double lx = __fma_rn(ed, LN2_HI, __fma_rn(ed, LN2_LO, logm));
+    const double t = __dmul_rn(y, lx);
+    if (t > 89.0) return inf;
+    if (t < -104.0) return 0.0f;
+    return __double2float_rn(exp_core(t));
 }
 
 }  // namespace pm

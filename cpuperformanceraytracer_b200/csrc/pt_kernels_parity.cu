@@ -29,7 +29,7 @@ cudaError_t occupancy_parity(const LaunchConfig& lc, int* blocks_per_sm)
 }
 
 // ---- parity hooks for the portable transcendentals (pm_math.cuh) ----------------------------
-// op: 0 sin, 1 cos, 2 atan2(a, b), 3 asin, 4 exp -- exactly what ParityMath hands the megakernel
+// op: 0 sin, 1 cos, 2 atan2(a, b), 3 asin, 4 exp -- exactly what ParityMath hands the megakernel; 9 pow(a, b) of the tone map
 __global__ void eval_portable_kernel(int op, const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n)
 {
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
@@ -39,6 +39,7 @@ __global__ void eval_portable_kernel(int op, const float* __restrict__ a, const 
         case 1: ParityMath::sincos(a[i], &t, &r); break;
         case 2: r = ParityMath::atan2(a[i], b[i]); break;
         case 3: r = ParityMath::asin(a[i]); break;
+        case 9: r = pm::powf_portable(a[i], b[i]); break;
         default: r = ParityMath::exp(a[i]); break;
         }
         out[i] = r;

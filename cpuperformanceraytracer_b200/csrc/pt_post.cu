@@ -27,7 +27,7 @@ __global__ void resolve_ldr_kernel(const float* __restrict__ target, uint32_t* _
     const int ly = r / groups_per_tile_row, gx = r - ly * groups_per_tile_row;
     const int x = tx * tile_w + gx * 8 + l, y = ty * tile_h + ly;
     const float* px = target + g * 24 + l;
-    out[(size_t)y * width + x] = tonemap::pack(px[0], px[8], px[16], mode);
+    out[(size_t)y * width + x] = tonemap::pack<true>(px[0], px[8], px[16], mode);
 }
 
 __global__ void scale_kernel(float* __restrict__ t, size_t n, float scale)

@@ -135,7 +135,7 @@ pt_render_sorted_kernel(const __grid_constant__ RenderParams p, const __grid_con
                     px[16] = avg.z;
                     const size_t idx = (size_t)(p.height - 1 - yflip) * p.width + x;
                     if (p.rng_out) p.rng_out[idx] = s.rng;
-                    if (p.screen) p.screen[idx] = tonemap::pack(avg.x, avg.y, avg.z, p.screen_mode);  // OUTPUT_TO_SCREEN
+                    if (p.screen) p.screen[idx] = tonemap::pack<false>(avg.x, avg.y, avg.z, p.screen_mode);  // OUTPUT_TO_SCREEN
                     live = false;
                 }
             }

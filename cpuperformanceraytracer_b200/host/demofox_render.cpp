@@ -39,8 +39,10 @@ b200pt_params params_for(int profile)
         p.output_to_screen = g_options.output_to_screen;
         p.exact_exp = !g_options.use_fast_approximate_exp;
         p.sincos_unit_vectors = !g_options.use_unit_vector_rejection_sampling;
-        p.exact_aces_tonemap = !g_options.use_fast_approximate_aces_tonemap;
     }
+    // CopyOutputToFile / OutputToScreen are the v4 translation unit's for every renderer (Application.cpp:381-398)
+    p.exact_tonemap = (g_options.use_fast_approximate_aces_tonemap ? 0 : B200PT_TONEMAP_EXACT_ACES) |
+                      (g_options.use_fast_approximate_gamma ? 0 : B200PT_TONEMAP_EXACT_GAMMA);
     return p;
 }
 

@@ -46,7 +46,9 @@ struct B200RenderOptions {
     int use_env_cubemap = USE_ENV_CUBEMAP;
     int use_random_jitter_texture_sampling = USE_RANDOM_JITTER_TEXTURE_SAMPLING;
     int output_to_screen = OUTPUT_TO_SCREEN;
-    // DemofoxRenderOptV4 only (the other variants' sources do not read them); 0 selects the exact variants
+    // 0 selects the exact variants.  The two tone-map switches act on CopyOutputToFile / OUTPUT_TO_SCREEN of every variant,
+    // the other two on DemofoxRenderOptV4 only (the other variants' sources do not read them)
+    int use_fast_approximate_gamma = USE_FAST_APPROXIMATE_GAMMA;
     int use_fast_approximate_aces_tonemap = USE_FAST_APPROXIMATE_ACES_TONEMAP;
     int use_fast_approximate_exp = USE_FAST_APPROXIMATE_EXP;
     int use_unit_vector_rejection_sampling = USE_UNIT_VECTOR_REJECTION_SAMPLING;

@@ -33,7 +33,7 @@
 #define ACCUMULATE_FRAMES 1  // :60 (always on in the kernel)
 #endif
 #ifndef USE_FAST_APPROXIMATE_GAMMA
-#define USE_FAST_APPROXIMATE_GAMMA 1  // :62 (the only variant implemented: pow_ps is an MSVC SVML routine)
+#define USE_FAST_APPROXIMATE_GAMMA 1  // :62
 #endif
 #ifndef USE_FAST_APPROXIMATE_ACES_TONEMAP
 #define USE_FAST_APPROXIMATE_ACES_TONEMAP 1  // :63

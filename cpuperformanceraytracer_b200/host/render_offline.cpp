@@ -7,7 +7,7 @@
 //   render_offline [--variant v4|v2|simt|v3redo|v3redo0] [--width W --height H --tiles-x X --tiles-y Y]
 //                  [--frames N] [--bounces B] [--env file.hdr | --cubemap px nx py ny pz nz]
 //                  [--bilinear] [--fast] [--per-frame-calls] [--out out.bmp] [--dump-f32 file]
-//                  [--exact-exp] [--sincos-unit-vectors] [--exact-aces]   (v4: global_preprocessor_flags.h:63-65 set to 0)
+//                  [--exact-exp] [--sincos-unit-vectors] [--exact-aces] [--exact-gamma]   (global_preprocessor_flags.h:62-65 set to 0)
 //                  [--gpus N [--shard spp|tiles] [--combine nccl|peer|fused]] [--device D]
 #include <chrono>
 #include <cstdio>
@@ -43,6 +43,7 @@ int main(int argc, char** argv)
         else if (a == "--exact-exp") opt.use_fast_approximate_exp = 0;
         else if (a == "--sincos-unit-vectors") opt.use_unit_vector_rejection_sampling = 0;
         else if (a == "--exact-aces") opt.use_fast_approximate_aces_tonemap = 0;
+        else if (a == "--exact-gamma") opt.use_fast_approximate_gamma = 0;
         else if (a == "--per-frame-calls") per_frame_calls = true;
         else if (a == "--gpus") opt.num_gpus = atoi(next());
         else if (a == "--device") opt.device = atoi(next());

@@ -84,8 +84,13 @@ enum {
 
 /* ScreenBufferData packing, ..._optimization_v4.cpp:1285-1290 (screen) / :1321-1325 (file) */
 enum { B200PT_LDR_FILE_RGBA = 0, B200PT_LDR_SCREEN_BGRA = 1,
-       B200PT_LDR_EXACT_ACES = 2 /* OR into either packing: the exact ACES curve (USE_FAST_APPROXIMATE_ACES_TONEMAP 0,
-                                    ..._optimization_v4.cpp:172-175) instead of the fast one (:168-171) */ };
+       /* OR into either packing (the values are b200pt_params.exact_tonemap << 1): */
+       B200PT_LDR_EXACT_ACES = 2,  /* the exact ACES curve (USE_FAST_APPROXIMATE_ACES_TONEMAP 0, ..._optimization_v4.cpp:172-175)
+                                      instead of the fast one (:168-171) */
+       B200PT_LDR_EXACT_GAMMA = 4  /* 1.055 pow(c, 1/2.4) - 0.055 (USE_FAST_APPROXIMATE_GAMMA 0, :185) instead of fast_pow_gamma
+                                      (:144-155); pow_ps is MSVC SVML in the reference, here the binary64 exp(y log x) the oracle
+                                      defines (oracle/portable_math.h pm_powf: the correctly rounded power on every tested input) */ };
+enum { B200PT_TONEMAP_EXACT_ACES = 1, B200PT_TONEMAP_EXACT_GAMMA = 2 }; /* bits of b200pt_params.exact_tonemap */
 
 /* mirrors struct texture, texture.h:6-12 (row-major RGB f32, row 0 = bottom after stbi's flip) */
 typedef struct b200pt_texture {
@@ -120,8 +125,9 @@ typedef struct b200pt_params {
                                        (1 + x/16.68)^16 approximation (..._optimization_v4.cpp:783-787) */
     int32_t sincos_unit_vectors;    /* 1: USE_UNIT_VECTOR_REJECTION_SAMPLING 0 -- RandomUnitVector (2 draws, sin/cos) and exact
                                        normalisations instead of the normalised cube sample (3 draws), :838-861 */
-    int32_t exact_aces_tonemap;     /* 1: USE_FAST_APPROXIMATE_ACES_TONEMAP 0 -- every tone map of this context (resolve_ldr,
-                                       present, OUTPUT_TO_SCREEN) uses the exact ACES curve, :172-175.  Any profile. */
+    int32_t exact_tonemap;          /* B200PT_TONEMAP_EXACT_ACES | _EXACT_GAMMA: USE_FAST_APPROXIMATE_ACES_TONEMAP 0 (:63) and / or
+                                       USE_FAST_APPROXIMATE_GAMMA 0 (:62) -- every tone map of this context (resolve_ldr, present,
+                                       OUTPUT_TO_SCREEN) uses the exact ACES curve (:172-175) / the pow() gamma (:185).  Any profile. */
 } b200pt_params;
 
 typedef struct b200pt_counters {
@@ -360,7 +366,8 @@ int b200pt_download_rng_state(b200pt_context* ctx, uint32_t* host_dst);
  * map sizes; a mismatch is also counted when an approximate angle strays more than a third of the bracket
  * half-width from the exact one; literal_path = lookups whose bracket was not decisive. */
 enum { B200PT_FN_SIN = 0, B200PT_FN_COS = 1, B200PT_FN_ATAN2 = 2, B200PT_FN_ASIN = 3, B200PT_FN_EXP = 4,
-       B200PT_FN_SQRT = 5, B200PT_FN_RCP = 6, B200PT_FN_DIV = 7, B200PT_FN_EQUIRECT_TEXEL = 8 /* 5-8: check_tiers only */ };
+       B200PT_FN_SQRT = 5, B200PT_FN_RCP = 6, B200PT_FN_DIV = 7, B200PT_FN_EQUIRECT_TEXEL = 8 /* 5-8: check_tiers only */,
+       B200PT_FN_POW = 9 /* eval only: pow(a, b) of the exact-gamma tone map (B200PT_LDR_EXACT_GAMMA) */ };
 int b200pt_eval_portable(b200pt_context* ctx, int fn, const float* a, const float* b, float* out, size_t n);
 int b200pt_check_portable_tiers(b200pt_context* ctx, int fn, uint64_t first, uint64_t count, uint64_t* mismatches,
                                 uint64_t* literal_path);

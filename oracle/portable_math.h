@@ -4,11 +4,12 @@
  * Bit-reproducible stand-ins for the closed-source MSVC SVML calls on the hot path
  * (reference mathlib.h:449-499: _mm256_sin_ps/_cos_ps/_sincos_ps/_atan2_ps/_asin_ps,
  * call sites demofox_path_tracing_v2.cpp:85-86, demofox_path_tracing_simt_textured.cpp:85-86,
- * texture.cpp:91,112,148-149,172-173,194-195).
+ * texture.cpp:91,112,148-149,172-173,194-195; _mm256_exp_ps: demofox_path_tracing_v3_redo.cpp:649-651 and v4's
+ * USE_FAST_APPROXIMATE_EXP 0; _mm256_pow_ps: v4's USE_FAST_APPROXIMATE_GAMMA 0, ..._optimization_v4.cpp:185).
  *
  * SVML is absent from /root/reference (it ships inside the MSVC v142 runtime, no version pin,
- * no source), so no golden vector pins this boundary: "parity unpinned" for these four
- * functions.  The oracle therefore DEFINES them: evaluated in IEEE binary64 with only
+ * no source), so no golden vector pins this boundary: "parity unpinned" for these
+ * functions (sin, cos, atan2, asin, exp, pow).  The oracle therefore DEFINES them: evaluated in IEEE binary64 with only
  * + - * / sqrt fma rint (every one of which is correctly rounded on x86-64 and on sm_100a),
  * then rounded once to binary32.  The CUDA parity kernel carries an independent copy of the
  * same algorithm (csrc/pm_math.cuh), so CPU and GPU agree bit for bit; tests/test_portable_math.py
@@ -140,12 +141,18 @@ static inline float pm_asinf(float v)
 /* exp of a binary32 argument (v3_redo absorption, demofox_path_tracing_v3_redo.cpp:649-651):
  * k = rint(x / ln 2), r = x - k ln 2 (two-part ln 2), degree-13 Taylor polynomial of exp(r),
  * |r| <= 0.347, scaled by 2^k through the exponent field, rounded once to binary32. */
+static inline double pm_exp_core(double x);
 static inline float pm_expf(float a)
 {
     double x = (double)a;
     if (x != x) return NAN;
     if (x > 89.0) return INFINITY;
     if (x < -104.0) return 0.0f;
+    return (float)pm_exp_core(x);
+}
+/* exp of a binary64 argument in [-104, 89], result in binary64 (not yet rounded to binary32) */
+static inline double pm_exp_core(double x)
+{
     const double LOG2E = 1.44269504088896338700e+00;
     const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
     double kd = __builtin_rint(x * LOG2E);
@@ -167,7 +174,54 @@ static inline float pm_expf(float a)
     p = PM_FMA(r, p, 1.0);
     union { uint64_t u; double d; } scale;
     scale.u = (uint64_t)((int64_t)kd + 1023) << 52;
-    return (float)(p * scale.d);
+    return p * scale.d;
+}
+
+/* pow(x, y) for x >= 0 (the non-fast gamma, pow_ps(rgb, 1/2.4), demofox_path_tracing_optimization_v4.cpp:185; SVML
+ * _mm256_pow_ps in the reference): exp(y * log x) in binary64, rounded once to binary32.
+ * log x: x = 2^e * m with m in [sqrt(1/2), sqrt(2)], s = (m - 1) / (m + 1), log m = 2 s (1 + z/3 + ... + z^10/21), z = s^2
+ * (|s| <= 0.1716: the first omitted term is below 2^-60 relative), log x = e * LN2_HI + (log m + e * LN2_LO) with e * LN2_HI
+ * exact.  The product y * log x carries <= 2^-52 relative error, so the binary32 result is the correctly rounded power except
+ * within ~|y log x| * 2^-28 ulp of a rounding boundary.  x < 0 -> NaN (the caller saturates to [0, 1] first). */
+static inline float pm_powf(float xf, float yf)
+{
+    double x = (double)xf, y = (double)yf;
+    if (y == 0.0 || x == 1.0) return 1.0f;
+    if (x != x || y != y || x < 0.0) return NAN;
+    if (x == 0.0) return y > 0.0 ? 0.0f : INFINITY;
+    if (x == INFINITY) return y > 0.0 ? INFINITY : 0.0f;
+    if (y == INFINITY) return x < 1.0 ? 0.0f : INFINITY;
+    if (y == -INFINITY) return x < 1.0 ? INFINITY : 0.0f;
+    union { double d; uint64_t u; } bits;
+    bits.d = x; /* a binary32 value is a normal binary64 number */
+    int64_t e = (int64_t)((bits.u >> 52) & 0x7ff) - 1023;
+    bits.u = (bits.u & 0x000fffffffffffffull) | 0x3ff0000000000000ull;
+    double m = bits.d; /* [1, 2) */
+    if (m > 1.41421356237309514547) {
+        m = m * 0.5;
+        e += 1;
+    }
+    const double s = (m - 1.0) / (m + 1.0);
+    const double z = s * s;
+    double p = 1.0 / 21.0;
+    p = PM_FMA(z, p, 1.0 / 19.0);
+    p = PM_FMA(z, p, 1.0 / 17.0);
+    p = PM_FMA(z, p, 1.0 / 15.0);
+    p = PM_FMA(z, p, 1.0 / 13.0);
+    p = PM_FMA(z, p, 1.0 / 11.0);
+    p = PM_FMA(z, p, 1.0 / 9.0);
+    p = PM_FMA(z, p, 1.0 / 7.0);
+    p = PM_FMA(z, p, 1.0 / 5.0);
+    p = PM_FMA(z, p, 1.0 / 3.0);
+    p = PM_FMA(z, p, 1.0);
+    const double logm = (s + s) * p;
+    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
+    const double ed = (double)e;
+    const double lx = PM_FMA(ed, LN2_HI, PM_FMA(ed, LN2_LO, logm));
+    const double t = y * lx;
+    if (t > 89.0) return INFINITY;
+    if (t < -104.0) return 0.0f;
+    return (float)pm_exp_core(t);
 }
 
 #ifdef __cplusplus

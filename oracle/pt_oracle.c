@@ -1118,6 +1118,11 @@ static float srgb1(float v)
     v = saturate1(v);
     return (v < 0.0031308f) ? v * 12.92f : FMA(1.055f, fast_pow_gamma(v), -0.055f);
 }
+static float srgb1_exact(float v) /* USE_FAST_APPROXIMATE_GAMMA 0, v4.cpp:185: 1.055f * pow_ps(rgb, 1.f / 2.4f) - 0.055f */
+{
+    v = saturate1(v);
+    return (v < 0.0031308f) ? v * 12.92f : 1.055f * pm_powf(v, 1.0f / 2.4f) - 0.055f;
+}
 
 int oracle_resolve_ldr(const float* target, int W, int H, int ntx, int nty, uint32_t* out, int mode)
 {
@@ -1128,7 +1133,8 @@ int oracle_resolve_ldr(const float* target, int W, int H, int ntx, int nty, uint
             float c[3] = {px[0], px[8], px[16]};
             uint32_t q[3];
             for (int k = 0; k < 3; k++) {
-                float v = srgb1((mode & 2) ? aces1_exact(c[k] * 1.0f) : aces1(c[k] * 1.0f));
+                float v = (mode & 2) ? aces1_exact(c[k] * 1.0f) : aces1(c[k] * 1.0f);
+                v = (mode & 4) ? srgb1_exact(v) : srgb1(v);
                 v = saturate1(v) * 255.f;
                 q[k] = (uint32_t)to_epi32(v) & 0xFFu;
             }
@@ -1172,6 +1178,10 @@ int oracle_max_segments(const oracle_params* p, int first_frame, int nframes, ui
             out[(size_t)y * p->width + x] = mx;
         }
     return 0;
+}
+void oracle_pm_powf_array(const float* x, const float* y, float* out, int64_t n)
+{
+    for (int64_t i = 0; i < n; i++) out[i] = pm_powf(x[i], y[i]);
 }
 void oracle_pm_expf_array(const float* x, float* out, int64_t n)
 {

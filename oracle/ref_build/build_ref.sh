@@ -6,8 +6,8 @@
 #   * "const int c_numBounces = N;"  -> "int c_numBounces = N;"      (harness sets --bounces)
 #   * "static f32 iFrame = 0.f;"     -> "f32 iFrame = 0.f;"          (harness sets --start-frame)
 #   * NUM_THREADS                    -> oracle_num_threads            (harness sets --threads)
-#   * v4 only: USE_FAST_APPROXIMATE_EXP / USE_UNIT_VECTOR_REJECTION_SAMPLING / USE_FAST_APPROXIMATE_ACES_TONEMAP are renamed
-#     ORACLE_<name> the same way (checked-in value 1 unless a variant says otherwise)
+#   * USE_FAST_APPROXIMATE_GAMMA / _ACES_TONEMAP / _EXP and USE_UNIT_VECTOR_REJECTION_SAMPLING (global_preprocessor_flags.h:62-65)
+#     are renamed ORACLE_<name> the same way (checked-in value 1 unless a variant says otherwise)
 #   * v3_redo only: "#define SCENE 1" -> "#ifndef SCENE / #define SCENE 1 / #endif" so that -DSCENE=0 selects the
 #     renderer's other checked-in scene (demofox_path_tracing_v3_redo.cpp:379,392-479,530-580)
 #   * v4 only: the compile-time switches of global_preprocessor_flags.h:56-66 that pick the env
@@ -27,7 +27,7 @@ fi
 
 # the three shading / tone-map switches keep their checked-in value (1) unless a variant overrides them
 BASE="-std=c++17 -O2 -mavx2 -mfma -fno-operator-names -fpermissive -w -I$HERE/stubs -I$HERE -I$HERE/.. -I$REF"
-DEFAULT_SWITCHES="-DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1"
+DEFAULT_SWITCHES="-DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 -DORACLE_USE_FAST_APPROXIMATE_GAMMA=1"
 flags_for_mode() { if [ "$1" = exact ]; then echo "-DORACLE_EXACT=1 -ffp-contract=off"; else echo "-DORACLE_EXACT=0"; fi; }
 
 PATCH=(-E
@@ -40,7 +40,8 @@ PATCH=(-E
   -e 's/^#if OUTPUT_TO_SCREEN/#if ORACLE_OUTPUT_TO_SCREEN/'
   -e 's/^#if USE_FAST_APPROXIMATE_EXP/#if ORACLE_USE_FAST_APPROXIMATE_EXP/'
   -e 's/^#if USE_UNIT_VECTOR_REJECTION_SAMPLING/#if ORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING/'
-  -e 's/^#if USE_FAST_APPROXIMATE_ACES_TONEMAP/#if ORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP/')
+  -e 's/^#if USE_FAST_APPROXIMATE_ACES_TONEMAP/#if ORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP/'
+  -e 's/^#if USE_FAST_APPROXIMATE_GAMMA/#if ORACLE_USE_FAST_APPROXIMATE_GAMMA/')
 
 compile_stream() { # $1=source file in $REF, $2=object, rest=flags
     local src="$1" obj="$2"; shift 2
@@ -77,11 +78,16 @@ for mode in exact asis; do
 done
 # the non-default shading / tone-map switches of global_preprocessor_flags.h:63-65 (exact mode only: parity anchors)
 build_variant ref_v4_equirect_random_expexact_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
-    -DORACLE_USE_FAST_APPROXIMATE_EXP=0 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 &
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=0 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 -DORACLE_USE_FAST_APPROXIMATE_GAMMA=1 &
 build_variant ref_v4_equirect_random_sincos_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
-    -DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=0 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 &
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=0 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 -DORACLE_USE_FAST_APPROXIMATE_GAMMA=1 &
 build_variant ref_v4_equirect_random_allexact_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
-    -DORACLE_USE_FAST_APPROXIMATE_EXP=0 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=0 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=0 &
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=0 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=0 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=0 -DORACLE_USE_FAST_APPROXIMATE_GAMMA=1 &
+# tone map only (the f32 buffer is the default build's): exact gamma alone, and exact gamma + exact ACES; pow_ps = portable_math.h's pm_powf
+build_variant ref_v4_equirect_random_gammaexact_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=1 -DORACLE_USE_FAST_APPROXIMATE_GAMMA=0 &
+build_variant ref_v4_equirect_random_ldrexact_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_RAND \
+    -DORACLE_USE_FAST_APPROXIMATE_EXP=1 -DORACLE_USE_UNIT_VECTOR_REJECTION_SAMPLING=1 -DORACLE_USE_FAST_APPROXIMATE_ACES_TONEMAP=0 -DORACLE_USE_FAST_APPROXIMATE_GAMMA=0 &
 build_variant ref_v4_equirect_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_EQ_BILIN &
 build_variant ref_v4_cubemap_bilinear_exact 3 demofox_path_tracing_optimization_v4.cpp exact $V4_CUBE_BILIN &
 # the reference's asset loader (stb_image / stb_image_write, vendored in the reference tree)

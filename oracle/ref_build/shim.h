@@ -76,18 +76,19 @@ ORACLE_LANEWISE1(_mm256_cos_ps, pm_cosf(x))
 ORACLE_LANEWISE1(_mm256_asin_ps, pm_asinf(x))
 ORACLE_LANEWISE2(_mm256_atan2_ps, pm_atan2f(x, y))
 ORACLE_LANEWISE1(_mm256_exp_ps, pm_expf(x))
+ORACLE_LANEWISE2(_mm256_pow_ps, pm_powf(x, y))
 #else
 ORACLE_LANEWISE1(_mm256_sin_ps, sinf(x))
 ORACLE_LANEWISE1(_mm256_cos_ps, cosf(x))
 ORACLE_LANEWISE1(_mm256_asin_ps, asinf(x))
 ORACLE_LANEWISE2(_mm256_atan2_ps, atan2f(x, y))
 ORACLE_LANEWISE1(_mm256_exp_ps, expf(x))
+ORACLE_LANEWISE2(_mm256_pow_ps, powf(x, y))
 #endif
 ORACLE_LANEWISE1(_mm256_tan_ps, tanf(x))
 ORACLE_LANEWISE1(_mm256_acos_ps, acosf(x))
 ORACLE_LANEWISE1(_mm256_atan_ps, atanf(x))
 ORACLE_LANEWISE1(_mm256_log_ps, logf(x))
-ORACLE_LANEWISE2(_mm256_pow_ps, powf(x, y))
 
 static inline __m256i _mm256_div_epi32(__m256i a_, __m256i b_)
 {

@@ -74,15 +74,19 @@ def main():
                           bounces=bounces, frames=frames, continued_frames=2, v4_flags=v4_flags))
         print(name, "mean", float(buf.mean()))
     # LDR goldens from the reference's CopyOutputToFile (single queue participant: deterministic); the second one is the
-    # build with USE_FAST_APPROXIMATE_ACES_TONEMAP 0 (and the other two switches off as well)
+    # build with USE_FAST_APPROXIMATE_ACES_TONEMAP 0 (and the two shading switches off as well), the last two are builds with
+    # USE_FAST_APPROXIMATE_GAMMA 0 alone and together with the exact ACES curve (pow_ps = portable_math.h's pm_powf).
+    # `ldr_mode` = the oracle_resolve_ldr mode bits (2 exact ACES, 4 exact gamma) that reproduce the file
     env = po.synthetic_env(128, 64)
-    for name, binary, exact_aces in (("v4_ldr", "ref_v4_equirect_random_exact", 0), ("v4_ldr_exact_aces", "ref_v4_equirect_random_allexact_exact", 1)):
+    for name, binary, exact_aces in (("v4_ldr", "ref_v4_equirect_random_exact", 0), ("v4_ldr_exact_aces", "ref_v4_equirect_random_allexact_exact", 1),
+                                     ("v4_ldr_exact_gamma", "ref_v4_equirect_random_gammaexact_exact", 0),
+                                     ("v4_ldr_exact_aces_gamma", "ref_v4_equirect_random_ldrexact_exact", 1)):
         if only is not None and name not in only:
             continue
         res = po.run_ref(binary, 128, 72, 4, 6, 6, bounces=8, env=env, threads=1, ldr=True)
         np.savez_compressed(os.path.join(HERE, name + ".npz"), buffer=res["buffer"], ldr=res["ldr"])
         index.append(dict(name=name, binary=binary, kind="ldr", width=128, height=72, ntx=4, nty=6, bounces=8, frames=6,
-                          env_shape=[128, 64], exact_aces=exact_aces))
+                          env_shape=[128, 64], exact_aces=exact_aces, ldr_mode=2 * exact_aces + (4 if "gamma" in name else 0)))
     with open(os.path.join(HERE, "index.json"), "w") as f:
         json.dump(index, f, indent=1)
 

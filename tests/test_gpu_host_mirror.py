@@ -95,11 +95,12 @@ def read_bmp24(path, w, h):
 
 
 def test_render_offline_v4_non_default_switches(oracle, io, tmp_path):
-    """--exact-exp / --sincos-unit-vectors / --exact-aces = USE_FAST_APPROXIMATE_EXP, USE_UNIT_VECTOR_REJECTION_SAMPLING,
-    USE_FAST_APPROXIMATE_ACES_TONEMAP set to 0 (global_preprocessor_flags.h:63-65): f32 dump and the written .bmp"""
+    """--exact-exp / --sincos-unit-vectors / --exact-aces / --exact-gamma = USE_FAST_APPROXIMATE_EXP, USE_UNIT_VECTOR_REJECTION_SAMPLING,
+    USE_FAST_APPROXIMATE_ACES_TONEMAP, USE_FAST_APPROXIMATE_GAMMA set to 0 (global_preprocessor_flags.h:62-65): f32 dump and the .bmp"""
     path, tex = make_equirect(tmp_path, oracle, io)
     for args, flags, aces in ((["--exact-exp"], oracle.V4_EXACT_EXP, 0), (["--sincos-unit-vectors"], oracle.V4_SINCOS_UNIT_VECTORS, 0),
-                              (["--exact-exp", "--sincos-unit-vectors", "--exact-aces"], 3, 2)):
+                              (["--exact-exp", "--sincos-unit-vectors", "--exact-aces"], 3, 2), (["--exact-gamma"], 0, 4),
+                              (["--exact-aces", "--exact-gamma"], 0, 6)):
         g, _ = run_cli(tmp_path, "--variant", "v4", "--env", path, *args, name="sw")
         o, _ = oracle.render(oracle.PROFILE_V4, W, H, NTX, NTY, 8, FRAMES + 2, env=tex, env_kind=oracle.ENV_EQUIRECT,
                              env_sampler=oracle.SAMPLER_RANDOM, v4_flags=flags)

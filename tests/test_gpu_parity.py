@@ -267,6 +267,46 @@ def test_exact_aces_tonemap_bit_exact(oracle):
         assert not np.array_equal(fast, exact)
 
 
+@pytest.mark.parametrize("aces,gamma", [(False, True), (True, True)])
+def test_exact_gamma_tonemap_bit_exact(oracle, aces, gamma):
+    """USE_FAST_APPROXIMATE_GAMMA 0 (global_preprocessor_flags.h:62), alone and with the exact ACES curve: resolve, OUTPUT_TO_SCREEN
+    (the resolve kernel runs behind the render kernel), the present ring, and per call on a default context"""
+    g = load_golden("v4_ldr_exact_aces_gamma" if aces else "v4_ldr_exact_gamma")
+    W, H, ntx, nty = 128, 72, 4, 6
+    mode = (2 if aces else 0) | 4
+    env = oracle.synthetic_env(128, 64)
+    with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=8, output_to_screen=True, env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM,
+                      exact_aces_tonemap=aces, exact_gamma=gamma) as r:
+        r.set_env(env)
+        r.resize(W, H, ntx, nty)
+        r.upload_target(g["buffer"])
+        assert np.array_equal(r.resolve_ldr(api.LDR_FILE_RGBA), g["ldr"])  # the reference build's CopyOutputToFile
+        assert np.array_equal(r.resolve_ldr(api.LDR_SCREEN_BGRA), oracle.resolve_ldr(g["buffer"], W, H, ntx, nty, mode=mode | 1))
+        buf = np.zeros(W * H * 3, dtype=np.float32)
+        scr = np.zeros((H, W), dtype=np.uint32)
+        r.frame_counter = 0
+        r.render_host(buf, W, H, ntx, nty, 6, screen=scr)
+        assert np.array_equal(buf, g["buffer"])
+        assert np.array_equal(scr, oracle.resolve_ldr(buf, W, H, ntx, nty, mode=mode | 1))
+        # progressive present: every presented frame is the tone map of the buffer after that frame
+        r.reset()
+        for k in range(1, 4):
+            r.present_submit(1)
+            frame = r.present_acquire()[0].copy()
+            o, _ = oracle.render(oracle.PROFILE_V4, W, H, ntx, nty, 8, k, env=env, env_kind=1, env_sampler=2)
+            assert np.array_equal(frame.reshape(H, W), oracle.resolve_ldr(o, W, H, ntx, nty, mode=mode | 1).reshape(H, W))
+    rng = np.random.default_rng(2)
+    W2, H2 = 2048, 64
+    vals = (rng.random(W2 * H2 * 3, dtype=np.float32) ** 3 * 4).astype(np.float32)
+    with api.Renderer(profile=api.PROFILE_V2) as r:
+        r.resize(W2, H2, 1, 1)
+        r.upload_target(vals)
+        for m in (api.LDR_EXACT_GAMMA, api.LDR_EXACT_GAMMA | api.LDR_EXACT_ACES, api.LDR_SCREEN_BGRA | api.LDR_EXACT_GAMMA):
+            assert np.array_equal(r.resolve_ldr(m), oracle.resolve_ldr(vals, W2, H2, 1, 1, mode=m))
+        with pytest.raises(api.B200PTError):
+            r.resolve_ldr(8)
+
+
 def test_sum_mode_matches_running_average(oracle):
     """ACCUM_SUM + finalize (the spp-shard epilogue) vs the sequential running average: different
     rounding order only; tolerance 2e-6 relative to the image scale (documented in DESIGN.md)."""

@@ -62,6 +62,20 @@ def test_device_values_equal_the_oracle_definitions(oracle):
         want = np.empty_like(e)
         L.oracle_pm_expf_array(_fp(e), _fp(want), i64(e.size))
         assert _same(r.eval_portable(api.FN_EXP, e), want)
+        # pow (the exact-gamma tone map, v4.cpp:185): the gamma's domain, other exponents, special values
+        L.oracle_pm_powf_array.argtypes = [ctypes.POINTER(ctypes.c_float)] * 3 + [i64]
+        px = np.concatenate([np.abs(unit), np.abs(bits[:500_000]), edge, np.abs(unit[:200_000]) * 100]).astype(np.float32)
+        for yv in (np.float32(1.0) / np.float32(2.4), np.float32(2.4), np.float32(-3.5), np.float32(0.0), np.float32(np.inf), np.float32(np.nan)):
+            py = np.full_like(px, yv)
+            want = np.empty_like(px)
+            L.oracle_pm_powf_array(_fp(px), _fp(py), _fp(want), i64(px.size))
+            assert _same(r.eval_portable(api.FN_POW, px, py), want), float(yv)
+        with np.errstate(invalid="ignore"):
+            py = np.abs(bits[500_000:500_000 + px.size]) % np.float32(40.0)  # arbitrary exponents in [0, 40)
+        py = np.where(np.isfinite(py), py, np.float32(1.5)).astype(np.float32)
+        want = np.empty_like(px)
+        L.oracle_pm_powf_array(_fp(px), _fp(py), _fp(want), i64(px.size))
+        assert _same(r.eval_portable(api.FN_POW, px, py), want)
 
 
 def test_first_tier_never_changes_a_result():

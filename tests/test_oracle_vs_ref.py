@@ -64,6 +64,20 @@ def test_v4_non_default_switches(oracle, name, flags):
 
 
 @needs_ref
+@pytest.mark.parametrize("name,mode", [("ref_v4_equirect_random_gammaexact_exact", 4), ("ref_v4_equirect_random_ldrexact_exact", 6)])
+def test_v4_exact_gamma_tonemap(oracle, name, mode):
+    """reference builds with USE_FAST_APPROXIMATE_GAMMA 0 (and ..._ACES_TONEMAP 0): CopyOutputToFile against the oracle's resolve"""
+    if po.ref_binary(name) is None:
+        pytest.skip(name + " not built")
+    W, H = 320, 180
+    env = po.synthetic_env(256, 128)
+    res = po.run_ref(name, W, H, 10, 15, 4, bounces=8, env=env, threads=1, ldr=True)
+    o, _ = oracle.render(po.PROFILE_V4, W, H, 10, 15, 8, 4, env=env, env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_RANDOM)
+    assert np.array_equal(res["buffer"], o)
+    assert np.array_equal(res["ldr"], oracle.resolve_ldr(o, W, H, 10, 15, mode=mode))
+
+
+@needs_ref
 @pytest.mark.parametrize("bounces,frames,tiles", [(8, 4, (2, 4)), (16, 2, (4, 2))])
 def test_v3_redo(oracle, bounces, frames, tiles):
     W, H = 256, 144

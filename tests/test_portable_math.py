@@ -80,3 +80,27 @@ def test_expf(oracle):
     o = np.empty_like(e)
     L.oracle_pm_expf_array(_fp(e), _fp(o), e.size)
     assert o[0] == 1.0 and o[1] == 0.0 and np.isinf(o[2]) and o[3] == np.float32(np.exp(np.float64(-103.0)))
+
+
+def test_powf(oracle):
+    """pm_powf (the pow_ps of the non-fast gamma, v4.cpp:185): the float64 power rounded to binary32 on the gamma's domain and beyond"""
+    L = oracle.lib()
+    L.oracle_pm_powf_array.argtypes = [ctypes.POINTER(ctypes.c_float)] * 3 + [ctypes.c_int64]
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.random(2_000_000, dtype=np.float32), (rng.random(300_000, dtype=np.float32) * 100).astype(np.float32),
+                        np.array([0.0031308, 1e-38, 1e-45, 3e38, 0.99999994, 1.0000001], np.float32)])
+    for yv in (np.float32(1.0) / np.float32(2.4), np.float32(2.4), np.float32(-3.5), np.float32(0.5), np.float32(17.25)):
+        y = np.full_like(x, yv)
+        out = np.empty_like(x)
+        L.oracle_pm_powf_array(_fp(x), _fp(y), _fp(out), x.size)
+        with np.errstate(all="ignore"):
+            ref = np.power(x.astype(np.float64), np.float64(yv)).astype(np.float32)
+        assert _ulp_diff(out, ref).max() <= 1 and (out == ref).mean() > 0.99999, float(yv)
+    # special values
+    e = np.array([0, 0, 1, 5, np.inf, np.inf, -1, np.nan, 2, 0.5, 2, 0.5, 7], np.float32)
+    p = np.array([2, -2, np.nan, 0, 2, -2, 0.5, 1, np.inf, np.inf, -np.inf, -np.inf, 1], np.float32)
+    o = np.empty_like(e)
+    L.oracle_pm_powf_array(_fp(e), _fp(p), _fp(o), e.size)
+    want = [0, np.inf, 1, 1, np.inf, 0, np.nan, np.nan, np.inf, 0, 0, np.inf, 7]
+    for got, w in zip(o, want):
+        assert (np.isnan(got) and np.isnan(w)) or got == np.float32(w)
