@@ -8,6 +8,8 @@ nvcc cross-compiles without a GPU.  Two translation units hold the megakernel, o
 arithmetic policy, because the policies need different code generation flags:
   pt_kernels_parity.cu  --fmad=false -prec-div=true -prec-sqrt=true -ftz=false
   pt_kernels_fast.cu    --fmad=true
+(and likewise pt_kernels_*_sorted.cu for the CTA-sorted scheduler, pt_kernels_*_v4sw.cu for the v4 kernels with the
+reference's non-default shading switches compiled in).
 """
 import os
 import shutil
@@ -40,6 +42,8 @@ UNITS = [
     (os.path.join(CSRC, "pt_kernels_fast.cu"), "pt_kernels_fast.o", ["--fmad=true"]),
     (os.path.join(CSRC, "pt_kernels_parity_sorted.cu"), "pt_kernels_parity_sorted.o", IEEE),
     (os.path.join(CSRC, "pt_kernels_fast_sorted.cu"), "pt_kernels_fast_sorted.o", ["--fmad=true"]),
+    (os.path.join(CSRC, "pt_kernels_parity_v4sw.cu"), "pt_kernels_parity_v4sw.o", IEEE),
+    (os.path.join(CSRC, "pt_kernels_fast_v4sw.cu"), "pt_kernels_fast_v4sw.o", ["--fmad=true"]),
     (os.path.join(CSRC, "pt_post.cu"), "pt_post.o", IEEE),
     (os.path.join(CSRC, "b200pt_capi.cu"), "b200pt_capi.o", IEEE),
     (os.path.join(CSRC, "b200pt_group.cu"), "b200pt_group.o", IEEE),

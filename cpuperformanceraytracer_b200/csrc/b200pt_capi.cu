@@ -37,8 +37,10 @@ LaunchConfig launch_config(const b200pt_context* c)
                                                                                                               : kSamplerPoint;
     lc.accum_mode = c->params.accum_mode;
     lc.static_scene = (c->params.generic_scene_tables || c->custom_scene) ? 0 : 1;
-    if (lc.profile == kProfileV4 && (c->params.exact_exp || c->params.sincos_unit_vectors)) lc.static_scene = 0;  // non-default switches
     if (lc.profile == kProfileV4 && lc.static_scene && !v4_scene_matches_static_tables(c->scenes.v4)) lc.static_scene = 0;
+    // the non-default shading switches: compiled into their own scene-specialised kernels (pt_kernels_*_v4sw.cu); the generic
+    // kernels read them from RenderParams::v4_flags
+    if (lc.profile == kProfileV4 && lc.static_scene) lc.v4_flags = (c->params.exact_exp ? 1 : 0) | (c->params.sincos_unit_vectors ? 2 : 0);
     if (lc.static_scene && lc.profile == kProfileV3Redo && !v3redo_spheres_match_static_tables(c->scenes.v3redo.sphere)) lc.static_scene = 0;
     if (lc.static_scene && lc.profile == kProfileV3RedoS0 && !v3redo0_spheres_match_static_tables(c->scenes.v3redo0.sphere)) lc.static_scene = 0;
     if (lc.static_scene && (lc.profile == kProfileV2 || lc.profile == kProfileSimtTextured) &&
@@ -259,7 +261,8 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
 
     LaunchConfig lc = launch_config(c);
     int bps = 0;
-    e = (c->params.math_mode == B200PT_MATH_PARITY) ? occupancy_parity(lc, &bps) : occupancy_fast(lc, &bps);
+    if (lc.v4_flags) e = (c->params.math_mode == B200PT_MATH_PARITY) ? occupancy_parity_v4sw(lc, &bps) : occupancy_fast_v4sw(lc, &bps);
+    else e = (c->params.math_mode == B200PT_MATH_PARITY) ? occupancy_parity(lc, &bps) : occupancy_fast(lc, &bps);
     if (e != cudaSuccess || bps <= 0) {
         b200pt_destroy(c);
         return B200PT_ERR_CUDA;
@@ -279,6 +282,7 @@ int b200pt_create(const b200pt_params* params, b200pt_context** out_ctx)
     c->sorted = sched == B200PT_SCHED_SORTED;
     if (c->sorted) {
         bps = 0;
+        if (lc.v4_flags) lc.static_scene = lc.v4_flags = 0;  // the sorted kernels take the switches at run time (generic kernel)
         e = (c->params.math_mode == B200PT_MATH_PARITY) ? occupancy_sorted_parity(lc, &bps) : occupancy_sorted_fast(lc, &bps);
         if (e != cudaSuccess || bps <= 0) {
             b200pt_destroy(c);
@@ -592,6 +596,7 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     // persistent grid: every SM holds blocks_per_sm resident CTAs; warps pull 32-pixel items
     // the sorted kernel packs the bounce count into 8 bits and the pixel coordinates into 16 each
     const bool sorted = c->sorted && rp.num_bounces <= 250 && rp.width <= 65535 && rp.height <= 65535;
+    if (sorted && lc.v4_flags) lc.static_scene = lc.v4_flags = 0;  // the sorted kernels take the switches at run time
     const int warps_per_block = (sorted ? 256 : lc.block) / 32;
     const int max_useful_blocks = (rp.num_items + warps_per_block - 1) / warps_per_block;
     lc.grid = c->sm_count * (sorted ? c->blocks_per_sm_sorted : c->blocks_per_sm);
@@ -606,6 +611,9 @@ static int render_frames_impl(b200pt_context* c, int32_t nframes, uint32_t* scre
     if (sorted)
         e = (c->params.math_mode == B200PT_MATH_PARITY) ? launch_render_sorted_parity(lc, rp, c->scenes, c->stream)
                                                         : launch_render_sorted_fast(lc, rp, c->scenes, c->stream);
+    else if (lc.v4_flags)
+        e = (c->params.math_mode == B200PT_MATH_PARITY) ? launch_render_parity_v4sw(lc, rp, c->scenes, c->stream)
+                                                        : launch_render_fast_v4sw(lc, rp, c->scenes, c->stream);
     else
         e = (c->params.math_mode == B200PT_MATH_PARITY) ? launch_render_parity(lc, rp, c->scenes, c->stream)
                                                         : launch_render_fast(lc, rp, c->scenes, c->stream);

@@ -240,6 +240,7 @@ __host__ __device__ constexpr int block_threads_for_profile(int profile)
 struct LaunchConfig {
     int profile, env_kind, env_sampler, accum_mode;
     int static_scene;  // Cornell profiles: vertex coordinates as immediates (same bits, fewer instructions)
+    int v4_flags;      // OPT_V4 + static_scene: the non-default shading switches compiled into the kernel (0 = the default kernels)
     int grid, block;
 };
 
@@ -254,6 +255,11 @@ cudaError_t launch_render_parity(const LaunchConfig& lc, const RenderParams& rp,
 cudaError_t launch_render_fast(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
 cudaError_t occupancy_parity(const LaunchConfig& lc, int* blocks_per_sm);
 cudaError_t occupancy_fast(const LaunchConfig& lc, int* blocks_per_sm);
+// pt_kernels_{parity,fast}_v4sw.cu: lc.v4_flags != 0
+cudaError_t launch_render_parity_v4sw(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
+cudaError_t launch_render_fast_v4sw(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
+cudaError_t occupancy_parity_v4sw(const LaunchConfig& lc, int* blocks_per_sm);
+cudaError_t occupancy_fast_v4sw(const LaunchConfig& lc, int* blocks_per_sm);
 // the CTA-sorted variant (pt_wavefront.cuh), in pt_kernels_parity_sorted.cu / pt_kernels_fast_sorted.cu
 cudaError_t launch_render_sorted_parity(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);
 cudaError_t launch_render_sorted_fast(const LaunchConfig& lc, const RenderParams& rp, const SceneSet& scenes, cudaStream_t stream);

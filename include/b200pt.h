@@ -119,8 +119,8 @@ typedef struct b200pt_params {
     int32_t disable_item_order;     /* 1: pull the work items in buffer order instead of scene-first / sky-last
                                        (A/B measurements; results are identical) */
     /* The reference's compile-time switches of global_preprocessor_flags.h:62-65, NON-default side; 0 keeps the checked-in
-     * defaults (all "fast").  The first two are OPT_V4 only (the other profiles' sources do not read them) and select the
-     * generic (table-driven) kernel, so expect the throughput of generic_scene_tables = 1. */
+     * defaults (all "fast").  The first two are OPT_V4 only (the other profiles' sources do not read them): scene-specialised
+     * kernels exist for every combination; with a run-time scene or B200PT_SCHED_SORTED the generic kernel reads them at run time. */
     int32_t exact_exp;              /* 1: USE_FAST_APPROXIMATE_EXP 0 -- Beer-Lambert absorption through exp_ps instead of the
                                        (1 + x/16.68)^16 approximation (..._optimization_v4.cpp:783-787) */
     int32_t sincos_unit_vectors;    /* 1: USE_UNIT_VECTOR_REJECTION_SAMPLING 0 -- RandomUnitVector (2 draws, sin/cos) and exact

@@ -188,18 +188,21 @@ SWITCH_CASES = [(1, 0, api.ENV_EQUIRECT, api.SAMPLER_RANDOM), (0, 1, api.ENV_CUB
 
 
 @pytest.mark.parametrize("exact_exp,sincos,ek,es", SWITCH_CASES)
-@pytest.mark.parametrize("sched", [api.SCHED_LANE, api.SCHED_SORTED])
-def test_non_default_switches_bit_exact_vs_oracle(oracle, exact_exp, sincos, ek, es, sched):
+@pytest.mark.parametrize("sched,generic", [(api.SCHED_LANE, False), (api.SCHED_LANE, True), (api.SCHED_SORTED, False)],
+                         ids=["static-kernel", "generic-kernel", "sorted"])
+def test_non_default_switches_bit_exact_vs_oracle(oracle, exact_exp, sincos, ek, es, sched, generic):
     """USE_FAST_APPROXIMATE_EXP 0 / USE_UNIT_VECTOR_REJECTION_SAMPLING 0 (global_preprocessor_flags.h:64-65): buffer, RNG
     states (2 + 2 draws per bounce instead of 3 + 3) and counters against the oracle, which is pinned on reference builds
-    with those switches flipped (tests/golden v4_exact_exp, v4_sincos_unit_vectors, v4_all_exact)"""
+    with those switches flipped (tests/golden v4_exact_exp, v4_sincos_unit_vectors, v4_all_exact).  Three kernels carry them:
+    the scene-specialised ones with the switches compiled in (pt_kernels_*_v4sw.cu), the generic per-lane kernel and the
+    generic CTA-sorted kernel (switches read at run time)"""
     import ctypes
     W, H, ntx, nty, frames, bounces = 256, 192, 4, 6, 10, 8
     env = None if ek == api.ENV_NONE else oracle.synthetic_env(*((64, 384) if ek == api.ENV_CUBEMAP else (256, 128)))
     flags = (oracle.V4_EXACT_EXP if exact_exp else 0) | (oracle.V4_SINCOS_UNIT_VECTORS if sincos else 0)
     o, oc = oracle.render(oracle.PROFILE_V4, W, H, ntx, nty, bounces, frames, env=env, env_kind=ek, env_sampler=es, v4_flags=flags)
     with api.Renderer(profile=api.PROFILE_OPT_V4, num_bounces=bounces, env_kind=ek, env_sampler=es, scheduler=sched,
-                      exact_exp=exact_exp, sincos_unit_vectors=sincos) as r:
+                      exact_exp=exact_exp, sincos_unit_vectors=sincos, generic_scene_tables=generic) as r:
         if env is not None:
             r.set_env(env)
         r.resize(W, H, ntx, nty)
