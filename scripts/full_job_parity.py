@@ -1,0 +1,85 @@
+#!/usr/bin/env python
+"""full_job_parity.py -- BASELINE.json configs[1] at its FULL size (Cornell P_v2, 1920x1080, 8 bounces, 1024 spp = 2.1e9 paths):
+the GPU's f32 accumulation buffer against (a) the reference's own code, `oracle/_ref/ref_v2_exact` (reference sources compiled
+in place, exact reciprocals; its v2 renderer takes at most 8 tiles = 8 threads, tiles 2x4), and (b) the C restatement
+`oracle/pt_oracle.c`, both run on the host cores of the GPU box while the GPU result waits.  Bit for bit, whole image.
+
+The parity tests in tests/ compare 1080p images at 6-16 frames and smaller images at more frames so that the suite runs in
+minutes; this script is the same comparison on the headline job itself (several CPU-minutes).  One JSON line.
+usage: full_job_parity.py [--spp 1024]"""
+import argparse
+import hashlib
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from cpuperformanceraytracer_b200 import api  # noqa: E402
+from oracle import pyoracle as po  # noqa: E402  (the checker)
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--spp", type=int, default=1024)
+ap.add_argument("--skip-oracle", action="store_true")
+a = ap.parse_args()
+W, H, NTX, NTY, BOUNCES, SPP = 1920, 1080, 2, 4, 8, a.spp
+
+with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES) as r:
+    r.resize(W, H, NTX, NTY)
+    r.render_frames(SPP)
+    gpu = r.download_target()
+    c = r.counters()
+    gpu_ms = c["last_render_ms"]
+with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES) as r:  # the bench's tiling (10x15): same pixels, other layout
+    r.resize(W, H, 10, 15)
+    r.render_frames(SPP)
+    gpu_1015 = r.download_target()
+
+res = {}
+
+
+def run_reference():
+    t0 = time.time()
+    if po.ref_binary("ref_v2_exact") is None:
+        res["ref"] = None
+        return
+    res["ref"] = po.run_ref("ref_v2_exact", W, H, NTX, NTY, SPP, bounces=BOUNCES, threads=8, timeout=7200)["buffer"]
+    res["ref_s"] = time.time() - t0
+
+
+def run_oracle():
+    t0 = time.time()
+    res["oracle"], res["oracle_counters"] = po.render(po.PROFILE_V2, W, H, NTX, NTY, BOUNCES, SPP, nthreads=max(1, (os.cpu_count() or 16) - 8))
+    res["oracle_s"] = time.time() - t0
+
+
+threads = [threading.Thread(target=run_reference)]
+if not a.skip_oracle:
+    threads.append(threading.Thread(target=run_oracle))
+for t in threads:
+    t.start()
+for t in threads:
+    t.join()
+
+
+def sha(b):
+    return hashlib.sha256(np.ascontiguousarray(b).tobytes()).hexdigest()[:16]
+
+
+out = {"job": f"Cornell P_v2 {W}x{H}, {BOUNCES} bounces, {SPP} spp, tiles {NTX}x{NTY} (the v2 renderer's 8-tile limit)",
+       "paths": W * H * SPP, "gpu_kernel_ms": gpu_ms, "gpu_sha256_16": sha(gpu), "host_cores": os.cpu_count(),
+       "gpu_tiles_10x15_same_pixels": bool(np.array_equal(po.detile(gpu, W, H, NTX, NTY), po.detile(gpu_1015, W, H, 10, 15)))}
+if res.get("ref") is not None:
+    out.update(reference="oracle/_ref/ref_v2_exact (8 threads)", reference_seconds=res["ref_s"], reference_sha256_16=sha(res["ref"]),
+               gpu_equals_reference_bit_for_bit=bool(np.array_equal(gpu, res["ref"])),
+               max_abs_diff_vs_reference=float(np.abs(gpu.astype(np.float64) - res["ref"]).max()))
+if "oracle" in res:
+    oc = res["oracle_counters"]
+    out.update(oracle_seconds=res["oracle_s"], oracle_sha256_16=sha(res["oracle"]), gpu_equals_oracle_bit_for_bit=bool(np.array_equal(gpu, res["oracle"])),
+               counters_equal=bool((c["segments"], c["escapes"]) == (oc["segments"], oc["escapes"])),
+               segments=oc["segments"], escapes=oc["escapes"])
+print(json.dumps(out), flush=True)
