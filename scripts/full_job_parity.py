@@ -6,7 +6,9 @@ in place, exact reciprocals; its v2 renderer takes at most 8 tiles = 8 threads, 
 
 The parity tests in tests/ compare 1080p images at 6-16 frames and smaller images at more frames so that the suite runs in
 minutes; this script is the same comparison on the headline job itself (several CPU-minutes).  One JSON line.
-usage: full_job_parity.py [--spp 1024]"""
+--profile v4: the reference's default renderer (demofox_path_tracing_optimization_v4.cpp, equirect env 2048x1024 synthetic,
+random-jitter sampler, tiles 10x15) at the same image size and sample count, against `ref_v4_equirect_random_exact` on all cores.
+usage: full_job_parity.py [--profile v2|v4] [--spp 1024] [--skip-oracle]"""
 import argparse
 import hashlib
 import json
@@ -25,35 +27,50 @@ from oracle import pyoracle as po  # noqa: E402  (the checker)
 ap = argparse.ArgumentParser()
 ap.add_argument("--spp", type=int, default=1024)
 ap.add_argument("--skip-oracle", action="store_true")
+ap.add_argument("--profile", default="v2", choices=["v2", "v4"])
 a = ap.parse_args()
-W, H, NTX, NTY, BOUNCES, SPP = 1920, 1080, 2, 4, 8, a.spp
+V4 = a.profile == "v4"
+W, H, BOUNCES, SPP = 1920, 1080, 8, a.spp
+NTX, NTY = (10, 15) if V4 else (2, 4)
+ENV = po.synthetic_env(2048, 1024) if V4 else None
+KW = dict(profile=api.PROFILE_OPT_V4, num_bounces=BOUNCES, env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM) if V4 else \
+    dict(profile=api.PROFILE_V2, num_bounces=BOUNCES)
+REF = "ref_v4_equirect_random_exact" if V4 else "ref_v2_exact"
+REF_THREADS = (os.cpu_count() or 16) if V4 else 8
+OPROFILE = po.PROFILE_V4 if V4 else po.PROFILE_V2
+OKW = dict(env=ENV, env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_RANDOM) if V4 else {}
 
-with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES) as r:
+with api.Renderer(**KW) as r:
+    if V4:
+        r.set_env(ENV)
     r.resize(W, H, NTX, NTY)
     r.render_frames(SPP)
     gpu = r.download_target()
     c = r.counters()
     gpu_ms = c["last_render_ms"]
-with api.Renderer(profile=api.PROFILE_V2, num_bounces=BOUNCES) as r:  # the bench's tiling (10x15): same pixels, other layout
-    r.resize(W, H, 10, 15)
+ALT = (2, 4) if V4 else (10, 15)
+with api.Renderer(**KW) as r:  # another tiling: same pixels, other layout
+    if V4:
+        r.set_env(ENV)
+    r.resize(W, H, *ALT)
     r.render_frames(SPP)
-    gpu_1015 = r.download_target()
+    gpu_alt = r.download_target()
 
 res = {}
 
 
 def run_reference():
     t0 = time.time()
-    if po.ref_binary("ref_v2_exact") is None:
+    if po.ref_binary(REF) is None:
         res["ref"] = None
         return
-    res["ref"] = po.run_ref("ref_v2_exact", W, H, NTX, NTY, SPP, bounces=BOUNCES, threads=8, timeout=7200)["buffer"]
+    res["ref"] = po.run_ref(REF, W, H, NTX, NTY, SPP, bounces=BOUNCES, env=ENV, threads=REF_THREADS, timeout=7200)["buffer"]
     res["ref_s"] = time.time() - t0
 
 
 def run_oracle():
     t0 = time.time()
-    res["oracle"], res["oracle_counters"] = po.render(po.PROFILE_V2, W, H, NTX, NTY, BOUNCES, SPP, nthreads=max(1, (os.cpu_count() or 16) - 8))
+    res["oracle"], res["oracle_counters"] = po.render(OPROFILE, W, H, NTX, NTY, BOUNCES, SPP, nthreads=max(1, (os.cpu_count() or 16) - 8), **OKW)
     res["oracle_s"] = time.time() - t0
 
 
@@ -70,11 +87,12 @@ def sha(b):
     return hashlib.sha256(np.ascontiguousarray(b).tobytes()).hexdigest()[:16]
 
 
-out = {"job": f"Cornell P_v2 {W}x{H}, {BOUNCES} bounces, {SPP} spp, tiles {NTX}x{NTY} (the v2 renderer's 8-tile limit)",
-       "paths": W * H * SPP, "gpu_kernel_ms": gpu_ms, "gpu_sha256_16": sha(gpu), "host_cores": os.cpu_count(),
-       "gpu_tiles_10x15_same_pixels": bool(np.array_equal(po.detile(gpu, W, H, NTX, NTY), po.detile(gpu_1015, W, H, 10, 15)))}
+JOB = (f"P_v4 + synthetic 2048x1024 equirect env, random-jitter sampler, {W}x{H}, {BOUNCES} bounces, {SPP} spp, tiles {NTX}x{NTY}" if V4 else
+       f"Cornell P_v2 {W}x{H}, {BOUNCES} bounces, {SPP} spp, tiles {NTX}x{NTY} (the v2 renderer's 8-tile limit)")
+out = {"job": JOB, "paths": W * H * SPP, "gpu_kernel_ms": gpu_ms, "gpu_sha256_16": sha(gpu), "host_cores": os.cpu_count(),
+       "gpu_tiles_%dx%d_same_pixels" % ALT: bool(np.array_equal(po.detile(gpu, W, H, NTX, NTY), po.detile(gpu_alt, W, H, *ALT)))}
 if res.get("ref") is not None:
-    out.update(reference="oracle/_ref/ref_v2_exact (8 threads)", reference_seconds=res["ref_s"], reference_sha256_16=sha(res["ref"]),
+    out.update(reference="oracle/_ref/%s (%d threads)" % (REF, REF_THREADS), reference_seconds=res["ref_s"], reference_sha256_16=sha(res["ref"]),
                gpu_equals_reference_bit_for_bit=bool(np.array_equal(gpu, res["ref"])),
                max_abs_diff_vs_reference=float(np.abs(gpu.astype(np.float64) - res["ref"]).max()))
 if "oracle" in res:
