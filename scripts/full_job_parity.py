@@ -8,7 +8,7 @@ The parity tests in tests/ compare 1080p images at 6-16 frames and smaller image
 minutes; this script is the same comparison on the headline job itself (several CPU-minutes).  One JSON line.
 --profile v4: the reference's default renderer (demofox_path_tracing_optimization_v4.cpp, equirect env 2048x1024 synthetic,
 random-jitter sampler, tiles 10x15) at the same image size and sample count, against `ref_v4_equirect_random_exact` on all cores.
-usage: full_job_parity.py [--profile v2|v4] [--spp 1024] [--skip-oracle]"""
+usage: full_job_parity.py [--profile v2|v4] [--spp 1024] [--width W --height H --bounces B] [--skip-oracle]"""
 import argparse
 import hashlib
 import json
@@ -28,10 +28,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--spp", type=int, default=1024)
 ap.add_argument("--skip-oracle", action="store_true")
 ap.add_argument("--profile", default="v2", choices=["v2", "v4"])
+ap.add_argument("--width", type=int, default=1920)   # BASELINE configs[4]: --width 8192 --height 8192 --bounces 16 (bounded --spp)
+ap.add_argument("--height", type=int, default=1080)
+ap.add_argument("--bounces", type=int, default=8)
 a = ap.parse_args()
 V4 = a.profile == "v4"
-W, H, BOUNCES, SPP = 1920, 1080, 8, a.spp
+W, H, BOUNCES, SPP = a.width, a.height, a.bounces, a.spp
 NTX, NTY = (10, 15) if V4 else (2, 4)
+if H % 15 or (W // 10) % 8:  # sizes the 10x15 grid does not divide (8192^2): 2x4 / 4x8
+    NTX, NTY = 2, 4
 ENV = po.synthetic_env(2048, 1024) if V4 else None
 KW = dict(profile=api.PROFILE_OPT_V4, num_bounces=BOUNCES, env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM) if V4 else \
     dict(profile=api.PROFILE_V2, num_bounces=BOUNCES)
@@ -48,7 +53,7 @@ with api.Renderer(**KW) as r:
     gpu = r.download_target()
     c = r.counters()
     gpu_ms = c["last_render_ms"]
-ALT = (2, 4) if V4 else (10, 15)
+ALT = (2, 4) if (NTX, NTY) != (2, 4) else ((10, 15) if H % 15 == 0 and (W // 10) % 8 == 0 else (4, 8))
 with api.Renderer(**KW) as r:  # another tiling: same pixels, other layout
     if V4:
         r.set_env(ENV)
