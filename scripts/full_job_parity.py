@@ -6,9 +6,9 @@ in place, exact reciprocals; its v2 renderer takes at most 8 tiles = 8 threads, 
 
 The parity tests in tests/ compare 1080p images at 6-16 frames and smaller images at more frames so that the suite runs in
 minutes; this script is the same comparison on the headline job itself (several CPU-minutes).  One JSON line.
---profile v4: the reference's default renderer (demofox_path_tracing_optimization_v4.cpp, equirect env 2048x1024 synthetic,
-random-jitter sampler, tiles 10x15) at the same image size and sample count, against `ref_v4_equirect_random_exact` on all cores.
-usage: full_job_parity.py [--profile v2|v4] [--spp 1024] [--width W --height H --bounces B] [--skip-oracle]"""
+--profile: any renderer / sampler the reference build exists for (v2, simt, v3redo, v3redo0, v4, v4_bilinear, v4_cubemap,
+v4_cubemap_bilinear); the v4 ones run the reference on all cores, the others on the 8 threads their tile table allows.
+usage: full_job_parity.py [--profile P] [--spp 1024] [--width W --height H --bounces B] [--skip-oracle]"""
 import argparse
 import hashlib
 import json
@@ -27,23 +27,38 @@ from oracle import pyoracle as po  # noqa: E402  (the checker)
 ap = argparse.ArgumentParser()
 ap.add_argument("--spp", type=int, default=1024)
 ap.add_argument("--skip-oracle", action="store_true")
-ap.add_argument("--profile", default="v2", choices=["v2", "v4"])
+# name -> (GPU profile kwargs, reference binary, its thread limit (None = all cores), oracle profile, oracle env kwargs, env shape, tiles)
+EQ, CUBE = (2048, 1024), (512, 3072)
+PROFILES = {
+    "v2": (dict(profile=api.PROFILE_V2), "ref_v2_exact", 8, po.PROFILE_V2, {}, None, (2, 4)),
+    "simt": (dict(profile=api.PROFILE_SIMT_TEXTURED), "ref_simt_textured_exact", 8, po.PROFILE_SIMT_TEXTURED, dict(env_kind=po.ENV_EQUIRECT), EQ, (2, 4)),
+    "v3redo": (dict(profile=api.PROFILE_V3_REDO), "ref_v3redo_exact", 8, po.PROFILE_V3REDO,
+               dict(env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_BILINEAR), EQ, (2, 4)),
+    "v3redo0": (dict(profile=api.PROFILE_V3_REDO_SCENE0), "ref_v3redo_scene0_exact", 8, po.PROFILE_V3REDO_SCENE0,
+                dict(env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_BILINEAR), EQ, (2, 4)),
+    "v4": (dict(profile=api.PROFILE_OPT_V4, env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM), "ref_v4_equirect_random_exact", None,
+           po.PROFILE_V4, dict(env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_RANDOM), EQ, (10, 15)),
+    "v4_bilinear": (dict(profile=api.PROFILE_OPT_V4, env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_BILINEAR), "ref_v4_equirect_bilinear_exact", None,
+                    po.PROFILE_V4, dict(env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_BILINEAR), EQ, (10, 15)),
+    "v4_cubemap": (dict(profile=api.PROFILE_OPT_V4, env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_RANDOM), "ref_v4_cubemap_random_exact", None,
+                   po.PROFILE_V4, dict(env_kind=po.ENV_CUBEMAP, env_sampler=po.SAMPLER_RANDOM), CUBE, (10, 15)),
+    "v4_cubemap_bilinear": (dict(profile=api.PROFILE_OPT_V4, env_kind=api.ENV_CUBEMAP, env_sampler=api.SAMPLER_BILINEAR), "ref_v4_cubemap_bilinear_exact",
+                            None, po.PROFILE_V4, dict(env_kind=po.ENV_CUBEMAP, env_sampler=po.SAMPLER_BILINEAR), CUBE, (10, 15)),
+}
+ap.add_argument("--profile", default="v2", choices=sorted(PROFILES))
 ap.add_argument("--width", type=int, default=1920)   # BASELINE configs[4]: --width 8192 --height 8192 --bounces 16 (bounded --spp)
 ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--bounces", type=int, default=8)
 a = ap.parse_args()
-V4 = a.profile == "v4"
+GKW, REF, REF_LIMIT, OPROFILE, OENV, ENV_SHAPE, (NTX, NTY) = PROFILES[a.profile]
+V4 = ENV_SHAPE is not None  # "has an env map"
 W, H, BOUNCES, SPP = a.width, a.height, a.bounces, a.spp
-NTX, NTY = (10, 15) if V4 else (2, 4)
-if H % 15 or (W // 10) % 8:  # sizes the 10x15 grid does not divide (8192^2): 2x4 / 4x8
+if H % NTY or (W // NTX) % 8 or W % NTX:  # sizes the 10x15 grid does not divide (8192^2, 3840x2160)
     NTX, NTY = 2, 4
-ENV = po.synthetic_env(2048, 1024) if V4 else None
-KW = dict(profile=api.PROFILE_OPT_V4, num_bounces=BOUNCES, env_kind=api.ENV_EQUIRECT, env_sampler=api.SAMPLER_RANDOM) if V4 else \
-    dict(profile=api.PROFILE_V2, num_bounces=BOUNCES)
-REF = "ref_v4_equirect_random_exact" if V4 else "ref_v2_exact"
-REF_THREADS = (os.cpu_count() or 16) if V4 else 8
-OPROFILE = po.PROFILE_V4 if V4 else po.PROFILE_V2
-OKW = dict(env=ENV, env_kind=po.ENV_EQUIRECT, env_sampler=po.SAMPLER_RANDOM) if V4 else {}
+ENV = po.synthetic_env(*ENV_SHAPE) if ENV_SHAPE else None
+KW = dict(num_bounces=BOUNCES, **GKW)
+REF_THREADS = REF_LIMIT or (os.cpu_count() or 16)
+OKW = dict(env=ENV, **OENV) if ENV_SHAPE else {}
 
 with api.Renderer(**KW) as r:
     if V4:
@@ -53,7 +68,7 @@ with api.Renderer(**KW) as r:
     gpu = r.download_target()
     c = r.counters()
     gpu_ms = c["last_render_ms"]
-ALT = (2, 4) if (NTX, NTY) != (2, 4) else ((10, 15) if H % 15 == 0 and (W // 10) % 8 == 0 else (4, 8))
+ALT = (2, 4) if (NTX, NTY) != (2, 4) else ((10, 15) if H % 15 == 0 and W % 10 == 0 and (W // 10) % 8 == 0 else (4, 8))
 with api.Renderer(**KW) as r:  # another tiling: same pixels, other layout
     if V4:
         r.set_env(ENV)
@@ -92,8 +107,8 @@ def sha(b):
     return hashlib.sha256(np.ascontiguousarray(b).tobytes()).hexdigest()[:16]
 
 
-JOB = (f"P_v4 + synthetic 2048x1024 equirect env, random-jitter sampler, {W}x{H}, {BOUNCES} bounces, {SPP} spp, tiles {NTX}x{NTY}" if V4 else
-       f"Cornell P_v2 {W}x{H}, {BOUNCES} bounces, {SPP} spp, tiles {NTX}x{NTY} (the v2 renderer's 8-tile limit)")
+JOB = f"profile {a.profile}, {W}x{H}, {BOUNCES} bounces, {SPP} spp, tiles {NTX}x{NTY}" + (
+    f", synthetic {ENV_SHAPE[0]}x{ENV_SHAPE[1]} env" if ENV_SHAPE else "") + (" (the renderer's 8-tile limit)" if REF_LIMIT else "")
 out = {"job": JOB, "paths": W * H * SPP, "gpu_kernel_ms": gpu_ms, "gpu_sha256_16": sha(gpu), "host_cores": os.cpu_count(),
        "gpu_tiles_%dx%d_same_pixels" % ALT: bool(np.array_equal(po.detile(gpu, W, H, NTX, NTY), po.detile(gpu_alt, W, H, *ALT)))}
 if res.get("ref") is not None:
