@@ -571,7 +571,8 @@ def main():
                        "rendered_per_step": f"one {WIDTH}x{HEIGHT} image of {spp} spp" + ("" if world == 1 else f", {spp}/{world} frames on each GPU"),
                        "sharding": "single GPU" if world == 1 else f"spp-shard x{world} of the fixed job: zero + render + NCCL all-reduce + 1/(N+1) scale inside the step",
                        "l2": "flushed between timed steps by a 256 MiB memset inside the timed region",
-                       "parity": "bit-exact vs oracle (math=parity)" if args.math == "parity" else "RMSE-bounded (math=fast)"},
+                       "parity": ("bit-exact vs oracle (math=parity); this very job against the reference build: profiles/r02_n_full_job_parity.json"
+                                  if args.math == "parity" else "RMSE-bounded (math=fast)")},
             "roofline": roofline,
             "e2e": e2e,
             "gpu_launches": launches,
