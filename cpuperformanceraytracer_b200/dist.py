@@ -9,7 +9,7 @@ so frames are independent streams and only the accumulation couples them.
              (B200PT_ACCUM_SUM); one all-reduce(sum) of the W*H*3 f32 buffer; then every rank
              scales by 1/(N+1) (b200pt_finalize_sum) -- the value the reference's running average
              reaches after N calls on a zeroed buffer.  Same samples, different summation order:
-             agrees with the sequential render to ~1e-6 relative (tests), not bit for bit.
+             agrees with the sequential render to ~sqrt(frames) x 2^-24 relative (6e-7 at 16 frames, 6e-6 at 1024), not bit for bit.
   tile-shard rank r renders tile rows [a, b) of every frame; the buffer is band-major (a row of
              tiles is contiguous, RenderTile v4.cpp:1189-1194) so each rank owns one contiguous
              span and an all-gather reassembles the image with no repacking.  Bit-identical to the
